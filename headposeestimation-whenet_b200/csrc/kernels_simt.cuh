@@ -1,0 +1,411 @@
+// kernels_simt.cuh - CUDA-core (fp32 FMA) kernels of the WHENet forward.
+//
+// These are the parity-mode kernels (fp32 storage) and the fallback family for
+// bf16/fp16 storage.  One kernel per logical op of SURVEY.md section 2.2:
+//   stem_kernel        u8/f32 NHWC -> conv3x3 s2 SAME + BN + swish          (reference whenet.py:25-27 front)
+//   pw_conv_kernel     1x1 conv as a tiled GEMM + BN bias (+swish) (+SE gate on A) (+residual)
+//   dw_conv_kernel     depthwise kxk SAME + BN + swish + deterministic SE partial sums
+//   se_gate_kernel     SE squeeze mean -> FC+swish -> FC+sigmoid
+//   head_pool_fc_decode_kernel  GAP(7x7) -> 3 Dense -> softmax -> expectation  (whenet.py:10-13, 28-33; utils.py:7-11)
+//
+// Activations are NHWC in the storage type T (float, __nv_bfloat16, __half);
+// all arithmetic is fp32.  BatchNorm is folded into the weights on the host
+// (scale into the kernel, shift into `bias`).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace whenet {
+
+// ----------------------------------------------------------------------------- storage helpers
+template <typename T> struct Store;
+template <> struct Store<float> {
+    static constexpr int VEC = 4;   // elements per 16-byte vector
+    __device__ static __forceinline__ float ld(const float* p) { return *p; }
+    __device__ static __forceinline__ void st(float* p, float v) { *p = v; }
+    __device__ static __forceinline__ float rnd(float v) { return v; }
+};
+template <> struct Store<__nv_bfloat16> {
+    static constexpr int VEC = 8;
+    __device__ static __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+    __device__ static __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+    __device__ static __forceinline__ float rnd(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+};
+template <> struct Store<__half> {
+    static constexpr int VEC = 8;
+    __device__ static __forceinline__ float ld(const __half* p) { return __half2float(*p); }
+    __device__ static __forceinline__ void st(__half* p, float v) { *p = __float2half_rn(v); }
+    __device__ static __forceinline__ float rnd(float v) { return __half2float(__float2half_rn(v)); }
+};
+
+// load / store 4 consecutive elements as fp32
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const __nv_bfloat16* p, float (&v)[4]) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x), b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    v[0] = fa.x; v[1] = fa.y; v[2] = fb.x; v[3] = fb.y;
+}
+__device__ __forceinline__ void ld4(const __half* p, float (&v)[4]) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    __half2 a = *reinterpret_cast<__half2*>(&t.x), b = *reinterpret_cast<__half2*>(&t.y);
+    float2 fa = __half22float2(a), fb = __half22float2(b);
+    v[0] = fa.x; v[1] = fa.y; v[2] = fb.x; v[3] = fb.y;
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(__nv_bfloat16* p, const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t; t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+}
+__device__ __forceinline__ void st4(__half* p, const float (&v)[4]) {
+    __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+    uint2 t; t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+}
+
+// 8 consecutive elements (16 B for 16-bit types, 2x16 B for float)
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float (&v)[8]) {
+    float a[4], b[4];
+    ld4(p, a); ld4(p + 4, b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] = a[i]; v[4 + i] = b[i]; }
+}
+template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <> __device__ __forceinline__ void ld8<__half>(const __half* p, float (&v)[8]) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <typename T> __device__ __forceinline__ void st8(T* p, const float (&v)[8]) {
+    float a[4] = {v[0], v[1], v[2], v[3]}, b[4] = {v[4], v[5], v[6], v[7]};
+    st4(p, a); st4(p + 4, b);
+}
+template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 t; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+}
+template <> __device__ __forceinline__ void st8<__half>(__half* p, const float (&v)[8]) {
+    uint4 t; __half2* h = reinterpret_cast<__half2*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+}
+
+// x * sigmoid(x).  expf (not __expf): the parity mode has to stay within 1e-2 deg.
+__device__ __forceinline__ float swish_f(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ----------------------------------------------------------------------------- stem
+// out[n,oy,ox,co] = swish( bias[co] + sum_{ky,kx,ci} w[ky,kx,ci,co] * norm(in[n,2oy+ky,2ox+kx,ci]) )
+// TF SAME for 224/k3/s2: pad_before 0, pad_after 1 -> the taps at index 224 read zero
+// IN NORMALISED SPACE (hard part 7), hence the explicit bounds test.
+// 4 threads per output pixel, 8 output channels each -> 16 B (bf16) coalesced stores.
+template <typename T, bool IN_U8>
+__global__ void __launch_bounds__(256) stem_kernel(const void* __restrict__ in_, T* __restrict__ out,
+                                                   const float* __restrict__ w,     // [27][32], BN-scale folded
+                                                   const float* __restrict__ bias,  // [32]
+                                                   const float* __restrict__ lut,   // [3][256] (IN_U8 only)
+                                                   int n_img) {
+    __shared__ float s_w[27 * 32];
+    __shared__ float s_lut[3 * 256];
+    for (int i = threadIdx.x; i < 27 * 32; i += 256) s_w[i] = w[i];
+    if (IN_U8)
+        for (int i = threadIdx.x; i < 768; i += 256) s_lut[i] = lut[i];
+    __syncthreads();
+    const long long total = (long long)n_img * 112 * 112 * 4;
+    long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (gid >= total) return;
+    const int cg = (int)(gid & 3);
+    long long pix = gid >> 2;
+    const int ox = (int)(pix % 112); pix /= 112;
+    const int oy = (int)(pix % 112);
+    const int n = (int)(pix / 112);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = bias[cg * 8 + i];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = 2 * oy + ky;
+        if (iy >= 224) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = 2 * ox + kx;
+            if (ix >= 224) continue;
+            const long long base = (((long long)n * 224 + iy) * 224 + ix) * 3;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                float x;
+                if (IN_U8) x = s_lut[ci * 256 + reinterpret_cast<const uint8_t*>(in_)[base + ci]];
+                else x = reinterpret_cast<const float*>(in_)[base + ci];
+                const float* wr = &s_w[((ky * 3 + kx) * 3 + ci) * 32 + cg * 8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(x, wr[i], acc[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = swish_f(acc[i]);
+    st8(out + (gid >> 2) * 32 + cg * 8, acc);
+}
+
+// ----------------------------------------------------------------------------- 1x1 conv (CUDA-core GEMM)
+// out[m, n] = act( bias[n] + sum_k A[m,k]*gate[m/hw, k] * W[k,n] ) (+ resid[m,n])
+// 64x64 tile, BK=16, 256 threads, 4x4 outputs per thread.  K and N are multiples of 8.
+template <typename T, bool SWISH, bool GATE, bool RESID>
+__global__ void __launch_bounds__(256) pw_conv_kernel(const T* __restrict__ A, const float* __restrict__ W,
+                                                      const float* __restrict__ bias, const float* __restrict__ gate,
+                                                      const T* __restrict__ resid, T* __restrict__ out,
+                                                      long long M, int K, int N, int hw) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int a_row = tid >> 2, a_k = (tid & 3) * 4;      // A tile: 64 rows x 16 k, 4 k per thread
+    const int b_k = tid >> 4, b_n = (tid & 15) * 4;       // B tile: 16 k x 64 n, 4 n per thread
+    const long long a_m = m0 + a_row;
+    const bool a_ok = a_m < M;
+    const float* gate_row = GATE ? gate + (a_ok ? (a_m / hw) : 0) * K : nullptr;
+
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        float av[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a_ok && k0 + a_k < K) {
+            ld4(A + a_m * K + k0 + a_k, av);
+            if (GATE) {
+                float g[4]; ld4(gate_row + k0 + a_k, g);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) av[i] *= g[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) As[a_k + i][a_row] = av[i];
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + b_k < K && n0 + b_n < N) bv = *reinterpret_cast<const float4*>(W + (long long)(k0 + b_k) * N + n0 + b_n);
+        *reinterpret_cast<float4*>(&Bs[b_k][b_n]) = bv;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    const int n = n0 + tx * 4;
+    if (n >= N) return;
+    float bb[4]; ld4(bias + n, bb);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long m = m0 + ty * 4 + i;
+        if (m >= M) break;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float x = acc[i][j] + bb[j];
+            v[j] = SWISH ? swish_f(x) : x;
+        }
+        if (RESID) {
+            float r[4]; ld4(resid + m * N + n, r);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] += r[j];
+        }
+        st4(out + m * N + n, v);
+    }
+}
+
+// ----------------------------------------------------------------------------- depthwise
+// out[n,oy,ox,c] = swish( bias[c] + sum_{ky,kx} w[ky,kx,c] * in[n, oy*S+ky-pad, ox*S+kx-pad, c] )
+// plus partial[n][tile][c] = sum over the tile's pixels of out (fp32, fixed order -> batch invariant).
+// block = (C/8 channel vectors, PY pixel lanes); grid = (tiles, N); a tile is ROWS output rows.
+template <typename T, int KS, int S>
+__global__ void __launch_bounds__(256) dw_conv_kernel(const T* __restrict__ in, const float* __restrict__ w,  // [KS*KS][C]
+                                                      const float* __restrict__ bias, T* __restrict__ out,
+                                                      float* __restrict__ partial,  // [N][tiles][C]
+                                                      int Hin, int Ho, int C, int pad, int rows) {
+    extern __shared__ float s_red[];   // [PY][C]
+    const int cv = threadIdx.x, py = threadIdx.y, PY = blockDim.y;
+    const int c0 = cv * 8;
+    const int n = blockIdx.y, tile = blockIdx.x;
+    const int r0 = tile * rows;
+    const int r1 = min(Ho, r0 + rows);
+    const int npix = (r1 - r0) * Ho;
+    const T* in_n = in + (long long)n * Hin * Hin * C;
+    T* out_n = out + (long long)n * Ho * Ho * C;
+    float bb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bb[i] = bias[c0 + i];
+    float sum[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum[i] = 0.f;
+    for (int p = py; p < npix; p += PY) {
+        const int oy = r0 + p / Ho, ox = p % Ho;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = bb[i];
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky) {
+            const int iy = oy * S + ky - pad;
+            if (iy < 0 || iy >= Hin) continue;
+#pragma unroll
+            for (int kx = 0; kx < KS; ++kx) {
+                const int ix = ox * S + kx - pad;
+                if (ix < 0 || ix >= Hin) continue;
+                float x[8], ww[8];
+                ld8(in_n + ((long long)iy * Hin + ix) * C + c0, x);
+                ld8(w + (ky * KS + kx) * C + c0, ww);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(x[i], ww[i], acc[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc[i] = swish_f(acc[i]); }
+        st8(out_n + ((long long)oy * Ho + ox) * C + c0, acc);
+        // the SE squeeze averages what the next layer will actually read: the stored (rounded) value
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sum[i] += Store<T>::rnd(acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_red[py * C + c0 + i] = sum[i];
+    __syncthreads();
+    if (py == 0) {
+        float tot[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot[i] = 0.f;
+        for (int y = 0; y < PY; ++y)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tot[i] += s_red[y * C + c0 + i];
+        float* dst = partial + ((long long)n * gridDim.x + tile) * C + c0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[i] = tot[i];
+    }
+}
+
+// ----------------------------------------------------------------------------- SE gate
+// mean[c] = sum_tiles partial / (Ho*Ho); h = swish(W1^T mean + b1); gate = sigmoid(W2^T h + b2)
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ partial, int tiles, float inv_hw,
+                                                      const float* __restrict__ w1t,  // [Cse][C]
+                                                      const float* __restrict__ b1,   // [Cse]
+                                                      const float* __restrict__ w2,   // [Cse][C]
+                                                      const float* __restrict__ b2,   // [C]
+                                                      float* __restrict__ gate,       // [N][C]
+                                                      int C, int Cse) {
+    extern __shared__ float sm[];   // mean[C] | hid[Cse]
+    float* mean = sm;
+    float* hid = sm + C;
+    const int n = blockIdx.x, tid = threadIdx.x;
+    for (int c = tid; c < C; c += 256) {
+        float s = 0.f;
+        for (int t = 0; t < tiles; ++t) s += partial[((long long)n * tiles + t) * C + c];
+        mean[c] = s * inv_hw;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int j = warp; j < Cse; j += 8) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(mean[c], w1t[(long long)j * C + c], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) hid[j] = swish_f(s + b1[j]);
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += 256) {
+        float s = b2[c];
+        for (int j = 0; j < Cse; ++j) s = fmaf(hid[j], w2[(long long)j * C + c], s);
+        gate[(long long)n * C + c] = sigmoid_f(s);
+    }
+}
+
+// ----------------------------------------------------------------------------- head: GAP + 3 Dense + softmax + expectation
+// feat: [N][49][1280] (post BN+swish head conv), or pooled sums when POOLED.
+// One CTA per crop.  angles[n] = {yaw, pitch, roll}; logits optional [N][252].
+template <typename T>
+__global__ void __launch_bounds__(256) head_pool_fc_decode_kernel(const T* __restrict__ feat, const float* __restrict__ pooled_in,
+                                                                 const float* __restrict__ wfc_t,  // [252][1280]
+                                                                 const float* __restrict__ bfc,    // [252]
+                                                                 float* __restrict__ angles, float* __restrict__ logits_out,
+                                                                 float* __restrict__ pooled_out) {
+    constexpr int C = 1280, NL = 252, HW = 49;
+    __shared__ float pooled[C];
+    __shared__ float logit[NL + 4];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    if (pooled_in) {
+        for (int c = tid; c < C; c += 256) pooled[c] = pooled_in[(long long)n * C + c];
+    } else {
+        const T* f = feat + (long long)n * HW * C;
+        for (int c = tid; c < C; c += 256) {
+            float s = 0.f;
+#pragma unroll 7
+            for (int p = 0; p < HW; ++p) s += Store<T>::ld(f + p * C + c);
+            pooled[c] = s * (1.0f / 49.0f);
+        }
+    }
+    __syncthreads();
+    if (pooled_out)
+        for (int c = tid; c < C; c += 256) pooled_out[(long long)n * C + c] = pooled[c];
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int j = warp; j < NL; j += 8) {
+        const float* wr = wfc_t + (long long)j * C;
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(pooled[c], wr[c], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) logit[j] = s + bfc[j];
+    }
+    __syncthreads();
+    if (logits_out)
+        for (int j = tid; j < NL; j += 256) logits_out[(long long)n * NL + j] = logit[j];
+    if (warp < 3) {
+        // reference utils.py:7-11 then whenet.py:31-33
+        const int off = warp == 0 ? 0 : (warp == 1 ? 120 : 186);
+        const int cnt = warp == 0 ? 120 : 66;
+        float mx = -INFINITY;
+        for (int j = lane; j < cnt; j += 32) mx = fmaxf(mx, logit[off + j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float se = 0.f, sw = 0.f;
+        for (int j = lane; j < cnt; j += 32) {
+            const float e = expf(logit[off + j] - mx);
+            se += e; sw = fmaf(e, (float)j, sw);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { se += __shfl_xor_sync(0xffffffffu, se, o); sw += __shfl_xor_sync(0xffffffffu, sw, o); }
+        if (lane == 0) angles[(long long)n * 3 + warp] = (sw / se) * 3.0f - (warp == 0 ? 180.0f : 99.0f);
+    }
+}
+
+// T -> float copy for debug taps
+template <typename T>
+__global__ void tap_copy_kernel(const T* __restrict__ src, float* __restrict__ dst, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = Store<T>::ld(src + i);
+}
+
+}  // namespace whenet

@@ -1,0 +1,733 @@
+// whenet_api.cu - context, weight packing, forward orchestration and the C ABI
+// declared in include/whenet_b200.h.  See DESIGN.md for the data layout.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/whenet_b200.h"
+#include "kernels_simt.cuh"
+#include "kernels_tc.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(WHENET_ECUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,         \
+                        cudaGetErrorString(e__));                                                  \
+    } while (0)
+
+constexpr double kBnEps = 1e-3;   // efficientnet==0.0.4 BatchNormalization epsilon
+constexpr int kImgElems = 224 * 224 * 3;
+
+struct BlockCfg {
+    int idx, hin, hout, cin, cexp, cout, k, s, cse, pad;
+    bool skip, has_expand;
+};
+
+// EfficientNet-B0 table (kernel, stride, expand, cin, cout, repeats); the python twin is arch.py.
+std::vector<BlockCfg> make_blocks() {
+    static const int st[7][6] = {{3, 1, 1, 32, 16, 1}, {3, 2, 6, 16, 24, 2}, {5, 2, 6, 24, 40, 2}, {3, 2, 6, 40, 80, 3},
+                                 {5, 1, 6, 80, 112, 3}, {5, 2, 6, 112, 192, 4}, {3, 1, 6, 192, 320, 1}};
+    std::vector<BlockCfg> v;
+    int h = 112, idx = 0;
+    for (auto& r : st)
+        for (int i = 0; i < r[5]; ++i) {
+            BlockCfg b{};
+            b.idx = ++idx;
+            b.k = r[0];
+            b.s = i == 0 ? r[1] : 1;
+            b.cin = i == 0 ? r[3] : r[4];
+            b.cout = r[4];
+            b.cexp = b.cin * r[2];
+            b.has_expand = r[2] != 1;
+            b.hin = h;
+            b.hout = (h + b.s - 1) / b.s;
+            b.cse = std::max(1, b.cin / 4);
+            b.skip = b.s == 1 && b.cin == b.cout;
+            int total = std::max((b.hout - 1) * b.s + b.k - b.hin, 0);
+            b.pad = total / 2;   // TF SAME: floor(total/2) before, the rest after
+            h = b.hout;
+            v.push_back(b);
+        }
+    return v;
+}
+
+struct BlockW {   // device pointers into the fp32 arena
+    float *w_exp = nullptr, *b_exp = nullptr;     // [cin][cexp], [cexp]
+    float *w_dw = nullptr, *b_dw = nullptr;       // [k*k][cexp], [cexp]
+    float *w_se1t = nullptr, *b_se1 = nullptr;    // [cse][cexp], [cse]
+    float *w_se2 = nullptr, *b_se2 = nullptr;     // [cse][cexp], [cexp]
+    float *w_proj = nullptr, *b_proj = nullptr;   // [cexp][cout], [cout]
+    void *wt_exp = nullptr, *wt_proj = nullptr;   // 16-bit [N][K] copies for the tensor-core path
+};
+
+struct EvPair { cudaEvent_t a, b; int stat; };
+struct Stat { std::string name; double bytes = 0, flops = 0; int launches = 0; float ms = 0; };
+
+}  // namespace
+
+struct whenet_ctx {
+    int device = 0, max_batch = 0, precision = 0;
+    int chunk = 0;          // crops per pass through the net
+    int use_tc = 0;         // tensor-core kernels for the 1x1 convs
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    bool weights_loaded = false;
+    std::vector<BlockCfg> blocks;
+    std::vector<BlockW> bw;
+    float* d_arena = nullptr;
+    void* d_arena16 = nullptr;
+    float *w_stem = nullptr, *b_stem = nullptr, *lut = nullptr;
+    float *w_head = nullptr, *b_head = nullptr, *w_fct = nullptr, *b_fc = nullptr;
+    void* wt_head = nullptr;
+    // workspaces
+    int ws_chunk = 0;
+    void *bufA = nullptr, *bufB = nullptr, *bufE = nullptr, *bufD = nullptr;
+    float *d_partial = nullptr, *d_gate = nullptr, *d_angles = nullptr, *d_logits = nullptr, *d_pooled = nullptr;
+    void* d_in[2] = {nullptr, nullptr};
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    // taps
+    bool taps_on = false;
+    std::map<std::string, std::pair<float*, size_t>> taps;
+    // profile
+    bool prof_on = false;
+    std::vector<EvPair> ev_used;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<Stat> stats;
+    std::map<std::string, int> stat_idx;
+    int64_t launches = 0;
+};
+
+namespace {
+
+size_t esize(int precision) { return precision == WHENET_PRECISION_FP32 ? 4 : 2; }
+
+// ----------------------------------------------------------------------------- profiling helpers
+struct Scope {
+    whenet_ctx* c;
+    int ev = -1;
+    Scope(whenet_ctx* ctx, const char* name, double bytes, double flops) : c(ctx) {
+        c->launches++;
+        if (!c->prof_on) return;
+        auto it = c->stat_idx.find(name);
+        int si;
+        if (it == c->stat_idx.end()) {
+            si = (int)c->stats.size();
+            Stat s; s.name = name;
+            c->stats.push_back(s);
+            c->stat_idx[name] = si;
+        } else si = it->second;
+        c->stats[si].bytes += bytes;
+        c->stats[si].flops += flops;
+        c->stats[si].launches++;
+        EvPair p{};
+        for (cudaEvent_t* e : {&p.a, &p.b}) {
+            if (!c->ev_pool.empty()) { *e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+            else cudaEventCreate(e);
+        }
+        p.stat = si;
+        cudaEventRecord(p.a, c->stream);
+        c->ev_used.push_back(p);
+        ev = (int)c->ev_used.size() - 1;
+    }
+    ~Scope() {
+        if (ev >= 0) cudaEventRecord(c->ev_used[ev].b, c->stream);
+    }
+};
+
+template <typename T>
+int add_tap(whenet_ctx* c, const std::string& name, const T* src, size_t n) {
+    auto it = c->taps.find(name);
+    if (it != c->taps.end() && it->second.second != n) {
+        cudaFree(it->second.first);
+        c->taps.erase(it);
+        it = c->taps.end();
+    }
+    float* dst;
+    if (it == c->taps.end()) {
+        CK(cudaMalloc(&dst, n * sizeof(float)));
+        c->taps[name] = {dst, n};
+    } else dst = it->second.first;
+    whenet::tap_copy_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(src, dst, (long long)n);
+    CK(cudaGetLastError());
+    return 0;
+}
+template <>
+int add_tap<float>(whenet_ctx* c, const std::string& name, const float* src, size_t n) {
+    auto it = c->taps.find(name);
+    if (it != c->taps.end() && it->second.second != n) {
+        cudaFree(it->second.first);
+        c->taps.erase(it);
+        it = c->taps.end();
+    }
+    float* dst;
+    if (it == c->taps.end()) {
+        CK(cudaMalloc(&dst, n * sizeof(float)));
+        c->taps[name] = {dst, n};
+    } else dst = it->second.first;
+    CK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- workspace
+void free_ws(whenet_ctx* c) {
+    for (void** p : {&c->bufA, &c->bufB, &c->bufE, &c->bufD, &c->d_in[0], &c->d_in[1]}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    for (float** p : {&c->d_partial, &c->d_gate, &c->d_pooled}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    c->ws_chunk = 0;
+}
+
+int ensure_ws(whenet_ctx* c) {
+    if (c->ws_chunk == c->chunk && c->bufA) return 0;
+    free_ws(c);
+    const size_t es = esize(c->precision), ch = (size_t)c->chunk;
+    // per-crop element counts: block io <= 112*112*32, expanded <= 112*112*96, dw out <= 112*112*32
+    const size_t io = 112ull * 112 * 32, ex = 112ull * 112 * 96, dw = 112ull * 112 * 32;
+    CK(cudaMalloc(&c->bufA, ch * io * es));
+    CK(cudaMalloc(&c->bufB, ch * io * es));
+    CK(cudaMalloc(&c->bufE, ch * ex * es));
+    CK(cudaMalloc(&c->bufD, ch * dw * es));
+    CK(cudaMalloc(&c->d_partial, ch * 16 * 1152 * sizeof(float)));   // <= 14 tiles x C (tiles*C <= 14*96.. ; 16*1152 bounds all)
+    CK(cudaMalloc(&c->d_gate, ch * 1152 * sizeof(float)));
+    CK(cudaMalloc(&c->d_pooled, ch * 1280 * sizeof(float)));
+    for (int i = 0; i < 2; ++i) CK(cudaMalloc(&c->d_in[i], ch * kImgElems * sizeof(float)));
+    c->ws_chunk = c->chunk;
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- launches
+template <typename T>
+int launch_pw(whenet_ctx* c, const char* name, const T* A, const float* W, const void* Wt16, const float* bias,
+              const float* gate, const T* resid, T* out, long long M, int K, int N, int hw, bool swish) {
+    const double bytes = (double)M * (K + N + (resid ? N : 0)) * sizeof(T);
+    const double flops = 2.0 * (double)M * K * N;
+    Scope sc(c, name, bytes, flops);
+    if (c->use_tc && Wt16 && sizeof(T) == 2) {
+        int rc = whenet::tc::launch_pw_tc<T>(c->stream, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish);
+        if (rc == 0) { CK(cudaGetLastError()); return 0; }
+        if (rc < 0) return fail(WHENET_ECUDA, "tensor-core 1x1 launch failed for %s (rc=%d)", name, rc);
+        // rc > 0: shape not supported by the tensor-core kernel -> CUDA-core kernel below
+    }
+    dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
+#define PW(SW, GA, RE) whenet::pw_conv_kernel<T, SW, GA, RE><<<grid, 256, 0, c->stream>>>(A, W, bias, gate, resid, out, M, K, N, hw)
+    if (swish && !gate && !resid) PW(true, false, false);
+    else if (!swish && gate && !resid) PW(false, true, false);
+    else if (!swish && gate && resid) PW(false, true, true);
+    else if (!swish && !gate && !resid) PW(false, false, false);
+    else return fail(WHENET_EINVAL, "unsupported 1x1 epilogue combination");
+#undef PW
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int launch_dw(whenet_ctx* c, const char* name, const BlockCfg& b, const BlockW& w, const T* in, T* out, int nb, int* tiles_out) {
+    const int rows = b.hout >= 28 ? 8 : b.hout;     // output rows per CTA
+    const int tiles = (b.hout + rows - 1) / rows;
+    *tiles_out = tiles;
+    const int cv = b.cexp / 8;
+    const int py = std::max(1, 256 / cv);
+    dim3 grid(tiles, nb), block(cv, py);
+    const size_t smem = (size_t)py * b.cexp * sizeof(float);
+    const double bytes = (double)nb * ((double)b.hin * b.hin + (double)b.hout * b.hout) * b.cexp * sizeof(T);
+    const double flops = 2.0 * nb * (double)b.hout * b.hout * b.k * b.k * b.cexp;
+    Scope sc(c, name, bytes, flops);
+#define DW(KS, S) whenet::dw_conv_kernel<T, KS, S><<<grid, block, smem, c->stream>>>(in, w.w_dw, w.b_dw, out, c->d_partial, b.hin, b.hout, b.cexp, b.pad, rows)
+    if (b.k == 3 && b.s == 1) DW(3, 1);
+    else if (b.k == 3 && b.s == 2) DW(3, 2);
+    else if (b.k == 5 && b.s == 1) DW(5, 1);
+    else if (b.k == 5 && b.s == 2) DW(5, 2);
+    else return fail(WHENET_EINVAL, "unsupported depthwise config");
+#undef DW
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, bool IN_U8>
+int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, float* d_logits, bool taps) {
+    char nm[48];
+    T* cur = (T*)c->bufA;
+    T* oth = (T*)c->bufB;
+    T* E = (T*)c->bufE;
+    T* D = (T*)c->bufD;
+    {
+        const long long total = (long long)nb * 112 * 112 * 4;
+        Scope sc(c, "stem", (double)nb * (kImgElems * (IN_U8 ? 1.0 : 4.0) + 112.0 * 112 * 32 * sizeof(T)),
+                 2.0 * nb * 112.0 * 112 * 27 * 32);
+        whenet::stem_kernel<T, IN_U8><<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_in, cur, c->w_stem, c->b_stem, c->lut, nb);
+        CK(cudaGetLastError());
+    }
+    if (taps) { int rc = add_tap<T>(c, "stem", cur, (size_t)nb * 112 * 112 * 32); if (rc) return rc; }
+    for (size_t i = 0; i < c->blocks.size(); ++i) {
+        const BlockCfg& b = c->blocks[i];
+        const BlockW& w = c->bw[i];
+        const T* dw_in = cur;
+        if (b.has_expand) {
+            snprintf(nm, sizeof nm, "b%02d.expand", b.idx);
+            int rc = launch_pw<T>(c, nm, cur, w.w_exp, w.wt_exp, w.b_exp, nullptr, nullptr, E,
+                                  (long long)nb * b.hin * b.hin, b.cin, b.cexp, b.hin * b.hin, true);
+            if (rc) return rc;
+            dw_in = E;
+        }
+        int tiles = 0;
+        snprintf(nm, sizeof nm, "b%02d.dw", b.idx);
+        int rc = launch_dw<T>(c, nm, b, w, dw_in, D, nb, &tiles);
+        if (rc) return rc;
+        {
+            snprintf(nm, sizeof nm, "b%02d.se", b.idx);
+            Scope sc(c, nm, (double)nb * (tiles + 1) * b.cexp * 4.0, 4.0 * nb * b.cexp * b.cse);
+            whenet::se_gate_kernel<<<nb, 256, (b.cexp + b.cse) * sizeof(float), c->stream>>>(
+                c->d_partial, tiles, 1.0f / (float)(b.hout * b.hout), w.w_se1t, w.b_se1, w.w_se2, w.b_se2, c->d_gate, b.cexp, b.cse);
+            CK(cudaGetLastError());
+        }
+        snprintf(nm, sizeof nm, "b%02d.project", b.idx);
+        rc = launch_pw<T>(c, nm, D, w.w_proj, w.wt_proj, w.b_proj, c->d_gate, b.skip ? cur : nullptr, oth,
+                          (long long)nb * b.hout * b.hout, b.cexp, b.cout, b.hout * b.hout, false);
+        if (rc) return rc;
+        if (taps) {
+            snprintf(nm, sizeof nm, "dw%d", b.idx);
+            if ((rc = add_tap<T>(c, nm, D, (size_t)nb * b.hout * b.hout * b.cexp))) return rc;
+            snprintf(nm, sizeof nm, "gate%d", b.idx);
+            if ((rc = add_tap<float>(c, nm, c->d_gate, (size_t)nb * b.cexp))) return rc;
+            snprintf(nm, sizeof nm, "block%d", b.idx);
+            if ((rc = add_tap<T>(c, nm, oth, (size_t)nb * b.hout * b.hout * b.cout))) return rc;
+        }
+        std::swap(cur, oth);
+    }
+    int rc = launch_pw<T>(c, "head.conv", cur, c->w_head, c->wt_head, c->b_head, nullptr, nullptr, E,
+                          (long long)nb * 49, 320, 1280, 49, true);
+    if (rc) return rc;
+    if (taps && (rc = add_tap<T>(c, "head", E, (size_t)nb * 49 * 1280))) return rc;
+    {
+        Scope sc(c, "head.fc_decode", (double)nb * (49.0 * 1280 * sizeof(T) + 12), 2.0 * nb * (1280.0 * 252 + 49 * 1280));
+        whenet::head_pool_fc_decode_kernel<T><<<nb, 256, 0, c->stream>>>(E, nullptr, c->w_fct, c->b_fc, d_angles, d_logits,
+                                                                         taps ? c->d_pooled : nullptr);
+        CK(cudaGetLastError());
+    }
+    if (taps && (rc = add_tap<float>(c, "pooled", c->d_pooled, (size_t)nb * 1280))) return rc;
+    return 0;
+}
+
+template <typename T, bool IN_U8>
+int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* angles_out, float* logits_out, int out_is_device) {
+    int rc = ensure_ws(c);
+    if (rc) return rc;
+    const size_t in_es = IN_U8 ? 1 : 4;
+    float* d_ang = out_is_device ? angles_out : c->d_angles;
+    float* d_log = logits_out ? (out_is_device ? logits_out : c->d_logits) : nullptr;
+    int ci = 0;
+    for (int off = 0; off < n; off += c->chunk, ++ci) {
+        const int nb = std::min(c->chunk, n - off);
+        const void* d_in;
+        const int slot = ci & 1;
+        if (in_is_device) {
+            d_in = (const char*)in + (size_t)off * kImgElems * in_es;
+        } else {
+            // stage through the copy stream so chunk i+1 uploads while chunk i computes
+            CK(cudaStreamWaitEvent(c->copy_stream, c->ev_free[slot], 0));
+            CK(cudaMemcpyAsync(c->d_in[slot], (const char*)in + (size_t)off * kImgElems * in_es, (size_t)nb * kImgElems * in_es,
+                               cudaMemcpyHostToDevice, c->copy_stream));
+            CK(cudaEventRecord(c->ev_ready[slot], c->copy_stream));
+            CK(cudaStreamWaitEvent(c->stream, c->ev_ready[slot], 0));
+            d_in = c->d_in[slot];
+        }
+        rc = forward_chunk<T, IN_U8>(c, d_in, nb, d_ang + (size_t)off * 3, d_log ? d_log + (size_t)off * WHENET_N_LOGITS : nullptr,
+                                     c->taps_on && off == 0 && nb <= 8);
+        if (rc) return rc;
+        if (!in_is_device) CK(cudaEventRecord(c->ev_free[slot], c->stream));
+    }
+    if (!out_is_device) {
+        CK(cudaMemcpyAsync(angles_out, c->d_angles, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (logits_out)
+            CK(cudaMemcpyAsync(logits_out, c->d_logits, (size_t)n * WHENET_N_LOGITS * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+template <bool IN_U8>
+int forward_dispatch(whenet_ctx* c, const void* in, int n, int in_is_device, float* angles_out, float* logits_out, int out_is_device) {
+    if (!c) return fail(WHENET_EINVAL, "null context");
+    if (!in || !angles_out) return fail(WHENET_EINVAL, "null input or output pointer");
+    if (n < 1 || n > c->max_batch) return fail(WHENET_EINVAL, "n=%d outside [1, max_batch=%d]", n, c->max_batch);
+    if (!c->weights_loaded) return fail(WHENET_ENOWEIGHTS, "whenet_load_weights has not been called");
+    CK(cudaSetDevice(c->device));
+    switch (c->precision) {
+        case WHENET_PRECISION_FP32: return forward_all<float, IN_U8>(c, in, n, in_is_device, angles_out, logits_out, out_is_device);
+        case WHENET_PRECISION_BF16: return forward_all<__nv_bfloat16, IN_U8>(c, in, n, in_is_device, angles_out, logits_out, out_is_device);
+        case WHENET_PRECISION_FP16: return forward_all<__half, IN_U8>(c, in, n, in_is_device, angles_out, logits_out, out_is_device);
+    }
+    return fail(WHENET_EINVAL, "bad precision %d", c->precision);
+}
+
+// ----------------------------------------------------------------------------- weight packing
+struct TensorMap {
+    std::map<std::string, const whenet_tensor*> m;
+    const whenet_tensor* get(const std::string& name, std::initializer_list<int64_t> dims, std::string* err) const {
+        auto it = m.find(name);
+        if (it == m.end()) { *err = "missing tensor " + name; return nullptr; }
+        const whenet_tensor* t = it->second;
+        bool ok = t->ndim == (int)dims.size();
+        int i = 0;
+        for (int64_t d : dims) { if (ok && t->dims[i] != d) ok = false; ++i; }
+        if (!ok || !t->data) { *err = "tensor " + name + " has the wrong shape"; return nullptr; }
+        return t;
+    }
+};
+
+struct BnFold { std::vector<double> scale, shift; };
+
+bool fold_bn(const TensorMap& tm, int bn_id, int c, BnFold* out, std::string* err) {
+    const std::string p = "batch_normalization_" + std::to_string(bn_id) + "/";
+    const whenet_tensor *g = tm.get(p + "gamma:0", {c}, err), *b = tm.get(p + "beta:0", {c}, err),
+                        *m = tm.get(p + "moving_mean:0", {c}, err), *v = tm.get(p + "moving_variance:0", {c}, err);
+    if (!g || !b || !m || !v) return false;
+    out->scale.resize(c);
+    out->shift.resize(c);
+    for (int i = 0; i < c; ++i) {
+        const double s = (double)g->data[i] / std::sqrt((double)v->data[i] + kBnEps);
+        out->scale[i] = s;
+        out->shift[i] = (double)b->data[i] - (double)m->data[i] * s;
+    }
+    return true;
+}
+
+template <typename T16> T16 to16(float v);
+template <> __nv_bfloat16 to16<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __half to16<__half>(float v) { return __float2half_rn(v); }
+
+}  // namespace
+
+// ============================================================================= C ABI
+extern "C" {
+
+const char* whenet_last_error(void) { return g_err; }
+const char* whenet_version(void) { return "whenet_b200 0.1 (sm_100a)"; }
+
+int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
+    if (!out) return fail(WHENET_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (max_batch < 1) return fail(WHENET_EINVAL, "max_batch must be >= 1");
+    if (precision < 0 || precision > 2) return fail(WHENET_EINVAL, "precision must be 0 (fp32), 1 (bf16) or 2 (fp16)");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(WHENET_EINVAL, "device %d not in [0,%d)", device, ndev);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(WHENET_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    whenet_ctx* c = new whenet_ctx();
+    c->device = device;
+    c->max_batch = max_batch;
+    c->precision = precision;
+    const char* ev = getenv("WHENET_CHUNK");
+    int chunk = ev ? atoi(ev) : 128;
+    if (chunk < 1) chunk = 128;
+    c->chunk = std::min(chunk, max_batch);
+    c->use_tc = precision != WHENET_PRECISION_FP32;
+    if (const char* e2 = getenv("WHENET_TC")) c->use_tc = atoi(e2) && precision != WHENET_PRECISION_FP32;
+    c->blocks = make_blocks();
+    c->bw.resize(c->blocks.size());
+    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+    }
+    CK(cudaMalloc(&c->d_angles, (size_t)max_batch * 3 * sizeof(float)));
+    CK(cudaMalloc(&c->d_logits, (size_t)max_batch * WHENET_N_LOGITS * sizeof(float)));
+    *out = c;
+    return 0;
+}
+
+int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tensors) {
+    if (!c || !tensors || n_tensors < 1) return fail(WHENET_EINVAL, "bad arguments");
+    CK(cudaSetDevice(c->device));
+    TensorMap tm;
+    for (int i = 0; i < n_tensors; ++i)
+        if (tensors[i].name) tm.m[tensors[i].name] = &tensors[i];
+    std::string err;
+    std::vector<float> arena;          // fp32 host staging; offsets recorded then rebased
+    std::vector<float> arena16src;     // values for the 16-bit [N][K] tensor-core copies
+    auto put = [&](const std::vector<float>& v) { size_t off = arena.size(); arena.insert(arena.end(), v.begin(), v.end());
+                                                  while (arena.size() % 4) arena.push_back(0.f); return off; };
+    auto put16 = [&](const std::vector<float>& v) { size_t off = arena16src.size(); arena16src.insert(arena16src.end(), v.begin(), v.end());
+                                                    while (arena16src.size() % 8) arena16src.push_back(0.f); return off; };
+    struct Off { size_t w_exp, b_exp, w_dw, b_dw, w_se1t, b_se1, w_se2, b_se2, w_proj, b_proj, t_exp, t_proj; };
+    std::vector<Off> offs(c->blocks.size());
+    int conv = 0, dwc = 0, bn = 0;
+    auto conv_name = [&]() { return "conv2d_" + std::to_string(++conv); };
+
+    // 1x1 conv [1,1,K,N] + BN(N) -> W'[K][N], bias[N], and the transposed [N][K] copy
+    auto pack_pw = [&](int K, int N, size_t* w_off, size_t* b_off, size_t* t_off) -> bool {
+        const std::string nm = conv_name();
+        const whenet_tensor* t = tm.get(nm + "/kernel:0", {1, 1, K, N}, &err);
+        if (!t) return false;
+        if (tm.m.count(nm + "/bias:0")) { err = nm + " unexpectedly has a bias"; return false; }
+        BnFold f;
+        if (!fold_bn(tm, ++bn, N, &f, &err)) return false;
+        std::vector<float> w((size_t)K * N), b(N), wt((size_t)K * N);
+        for (int k = 0; k < K; ++k)
+            for (int n = 0; n < N; ++n) {
+                const float v = (float)((double)t->data[(size_t)k * N + n] * f.scale[n]);
+                w[(size_t)k * N + n] = v;
+                wt[(size_t)n * K + k] = v;
+            }
+        for (int n = 0; n < N; ++n) b[n] = (float)f.shift[n];
+        *w_off = put(w);
+        *b_off = put(b);
+        *t_off = put16(wt);
+        return true;
+    };
+
+    // ---- stem: conv2d_1 [3,3,3,32] + BN1
+    size_t o_wstem, o_bstem, o_lut;
+    {
+        const whenet_tensor* t = tm.get(conv_name() + "/kernel:0", {3, 3, 3, 32}, &err);
+        BnFold f;
+        if (!t || !fold_bn(tm, ++bn, 32, &f, &err)) return fail(WHENET_ESHAPE, "%s", err.c_str());
+        std::vector<float> w(27 * 32), b(32), lut(768);
+        for (int i = 0; i < 27; ++i)
+            for (int co = 0; co < 32; ++co) w[i * 32 + co] = (float)((double)t->data[i * 32 + co] * f.scale[co]);
+        for (int co = 0; co < 32; ++co) b[co] = (float)f.shift[co];
+        // reference whenet.py:23-26, evaluated in float64 like numpy, then the float32 feed cast
+        const double mean[3] = {0.485, 0.456, 0.406}, sd[3] = {0.229, 0.224, 0.225};
+        for (int ch = 0; ch < 3; ++ch)
+            for (int v = 0; v < 256; ++v) lut[ch * 256 + v] = (float)((((double)v / 255.0) - mean[ch]) / sd[ch]);
+        o_wstem = put(w); o_bstem = put(b); o_lut = put(lut);
+    }
+    // ---- 16 MBConv blocks
+    for (size_t i = 0; i < c->blocks.size(); ++i) {
+        const BlockCfg& b = c->blocks[i];
+        Off& o = offs[i];
+        if (b.has_expand) {
+            if (!pack_pw(b.cin, b.cexp, &o.w_exp, &o.b_exp, &o.t_exp)) return fail(WHENET_ESHAPE, "%s", err.c_str());
+        }
+        {
+            const std::string nm = "depthwise_conv2d_" + std::to_string(++dwc);
+            const whenet_tensor* t = tm.get(nm + "/depthwise_kernel:0", {b.k, b.k, b.cexp, 1}, &err);
+            BnFold f;
+            if (!t || !fold_bn(tm, ++bn, b.cexp, &f, &err)) return fail(WHENET_ESHAPE, "%s", err.c_str());
+            std::vector<float> w((size_t)b.k * b.k * b.cexp), bb(b.cexp);
+            for (int tap = 0; tap < b.k * b.k; ++tap)
+                for (int ch = 0; ch < b.cexp; ++ch) w[(size_t)tap * b.cexp + ch] = (float)((double)t->data[(size_t)tap * b.cexp + ch] * f.scale[ch]);
+            for (int ch = 0; ch < b.cexp; ++ch) bb[ch] = (float)f.shift[ch];
+            o.w_dw = put(w); o.b_dw = put(bb);
+        }
+        {
+            const std::string n1 = conv_name();
+            const whenet_tensor *w1 = tm.get(n1 + "/kernel:0", {1, 1, b.cexp, b.cse}, &err), *b1 = tm.get(n1 + "/bias:0", {b.cse}, &err);
+            const std::string n2 = conv_name();
+            const whenet_tensor *w2 = tm.get(n2 + "/kernel:0", {1, 1, b.cse, b.cexp}, &err), *b2 = tm.get(n2 + "/bias:0", {b.cexp}, &err);
+            if (!w1 || !b1 || !w2 || !b2) return fail(WHENET_ESHAPE, "%s", err.c_str());
+            std::vector<float> w1t((size_t)b.cse * b.cexp);
+            for (int ch = 0; ch < b.cexp; ++ch)
+                for (int j = 0; j < b.cse; ++j) w1t[(size_t)j * b.cexp + ch] = w1->data[(size_t)ch * b.cse + j];
+            o.w_se1t = put(w1t);
+            o.b_se1 = put(std::vector<float>(b1->data, b1->data + b.cse));
+            o.w_se2 = put(std::vector<float>(w2->data, w2->data + (size_t)b.cse * b.cexp));
+            o.b_se2 = put(std::vector<float>(b2->data, b2->data + b.cexp));
+        }
+        if (!pack_pw(b.cexp, b.cout, &o.w_proj, &o.b_proj, &o.t_proj)) return fail(WHENET_ESHAPE, "%s", err.c_str());
+    }
+    // ---- head conv + BN49, three Dense heads
+    size_t o_whead, o_bhead, o_thead, o_wfct, o_bfc;
+    if (!pack_pw(320, 1280, &o_whead, &o_bhead, &o_thead)) return fail(WHENET_ESHAPE, "%s", err.c_str());
+    {
+        std::vector<float> wt((size_t)WHENET_N_LOGITS * 1280), bb(WHENET_N_LOGITS);
+        const char* names[3] = {"yaw_new", "pitch_new", "roll_new"};   // reference whenet.py:11-13
+        const int units[3] = {WHENET_N_YAW, WHENET_N_PITCH, WHENET_N_ROLL};
+        int row = 0;
+        for (int h = 0; h < 3; ++h) {
+            const whenet_tensor *k = tm.get(std::string(names[h]) + "/kernel:0", {1280, units[h]}, &err),
+                                *bi = tm.get(std::string(names[h]) + "/bias:0", {units[h]}, &err);
+            if (!k || !bi) return fail(WHENET_ESHAPE, "%s", err.c_str());
+            for (int u = 0; u < units[h]; ++u, ++row) {
+                for (int ch = 0; ch < 1280; ++ch) wt[(size_t)row * 1280 + ch] = k->data[(size_t)ch * units[h] + u];
+                bb[row] = bi->data[u];
+            }
+        }
+        o_wfct = put(wt); o_bfc = put(bb);
+    }
+    if (conv != 65 || dwc != 16 || bn != 49)
+        return fail(WHENET_ESHAPE, "consumed %d/%d/%d conv/dw/bn layers, expected 65/16/49", conv, dwc, bn);
+
+    // ---- upload
+    if (c->d_arena) { cudaFree(c->d_arena); c->d_arena = nullptr; }
+    if (c->d_arena16) { cudaFree(c->d_arena16); c->d_arena16 = nullptr; }
+    CK(cudaMalloc(&c->d_arena, arena.size() * sizeof(float)));
+    CK(cudaMemcpy(c->d_arena, arena.data(), arena.size() * sizeof(float), cudaMemcpyHostToDevice));
+    char* base16 = nullptr;
+    if (c->precision != WHENET_PRECISION_FP32) {
+        std::vector<uint16_t> h16(arena16src.size());
+        for (size_t i = 0; i < h16.size(); ++i) {
+            if (c->precision == WHENET_PRECISION_BF16) { __nv_bfloat16 v = to16<__nv_bfloat16>(arena16src[i]); memcpy(&h16[i], &v, 2); }
+            else { __half v = to16<__half>(arena16src[i]); memcpy(&h16[i], &v, 2); }
+        }
+        CK(cudaMalloc(&c->d_arena16, h16.size() * 2 + 256));
+        CK(cudaMemcpy(c->d_arena16, h16.data(), h16.size() * 2, cudaMemcpyHostToDevice));
+        base16 = (char*)c->d_arena16;
+    }
+    float* A = c->d_arena;
+    c->w_stem = A + o_wstem; c->b_stem = A + o_bstem; c->lut = A + o_lut;
+    for (size_t i = 0; i < c->blocks.size(); ++i) {
+        const Off& o = offs[i];
+        BlockW& w = c->bw[i];
+        if (c->blocks[i].has_expand) {
+            w.w_exp = A + o.w_exp; w.b_exp = A + o.b_exp;
+            w.wt_exp = base16 ? base16 + o.t_exp * 2 : nullptr;
+        }
+        w.w_dw = A + o.w_dw; w.b_dw = A + o.b_dw;
+        w.w_se1t = A + o.w_se1t; w.b_se1 = A + o.b_se1; w.w_se2 = A + o.w_se2; w.b_se2 = A + o.b_se2;
+        w.w_proj = A + o.w_proj; w.b_proj = A + o.b_proj;
+        w.wt_proj = base16 ? base16 + o.t_proj * 2 : nullptr;
+    }
+    c->w_head = A + o_whead; c->b_head = A + o_bhead; c->wt_head = base16 ? base16 + o_thead * 2 : nullptr;
+    c->w_fct = A + o_wfct; c->b_fc = A + o_bfc;
+    c->weights_loaded = true;
+    return 0;
+}
+
+int whenet_set_stream(whenet_ctx* c, void* s) {
+    if (!c) return fail(WHENET_EINVAL, "null context");
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return 0;
+}
+
+int whenet_forward_u8(whenet_ctx* c, const uint8_t* in, int n, int in_is_device, float* angles, float* logits, int out_is_device) {
+    return forward_dispatch<true>(c, in, n, in_is_device, angles, logits, out_is_device);
+}
+
+int whenet_forward_f32(whenet_ctx* c, const float* in, int n, int in_is_device, float* angles, float* logits, int out_is_device) {
+    return forward_dispatch<false>(c, in, n, in_is_device, angles, logits, out_is_device);
+}
+
+int whenet_synchronize(whenet_ctx* c) {
+    if (!c) return fail(WHENET_EINVAL, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+void* whenet_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        fail(WHENET_ECUDA, "cudaHostAlloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+void whenet_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int whenet_debug_enable_taps(whenet_ctx* c, int enable) {
+    if (!c) return fail(WHENET_EINVAL, "null context");
+    c->taps_on = enable != 0;
+    return 0;
+}
+
+int whenet_debug_tap(whenet_ctx* c, const char* name, float* out, size_t cap, size_t* n_elems) {
+    if (!c || !name) return fail(WHENET_EINVAL, "bad arguments");
+    auto it = c->taps.find(name);
+    if (it == c->taps.end()) return fail(WHENET_ENOTFOUND, "no tap named %s (enable taps and run a forward with n<=8)", name);
+    if (n_elems) *n_elems = it->second.second;
+    if (!out) return 0;
+    if (cap < it->second.second) return fail(WHENET_EINVAL, "tap %s needs %zu elements, buffer holds %zu", name, it->second.second, cap);
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out, it->second.first, it->second.second * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int whenet_profile_enable(whenet_ctx* c, int enable) {
+    if (!c) return fail(WHENET_EINVAL, "null context");
+    c->prof_on = enable != 0;
+    return 0;
+}
+
+int whenet_profile_read(whenet_ctx* c, whenet_kernel_stat* out, int cap) {
+    if (!c) return fail(WHENET_EINVAL, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (auto& p : c->ev_used) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) c->stats[p.stat].ms += ms;
+        c->ev_pool.push_back(p.a);
+        c->ev_pool.push_back(p.b);
+    }
+    c->ev_used.clear();
+    int n = 0;
+    for (auto& s : c->stats) {
+        if (out && n < cap) {
+            memset(&out[n], 0, sizeof(out[n]));
+            snprintf(out[n].name, sizeof(out[n].name), "%s", s.name.c_str());
+            out[n].ms = s.ms; out[n].launches = s.launches; out[n].bytes = s.bytes; out[n].flops = s.flops;
+        }
+        ++n;
+    }
+    if (out) { c->stats.clear(); c->stat_idx.clear(); }
+    return n;
+}
+
+int64_t whenet_launch_count(whenet_ctx* c) { return c ? c->launches : 0; }
+
+int whenet_set_option(whenet_ctx* c, const char* key, int value) {
+    if (!c || !key) return fail(WHENET_EINVAL, "bad arguments");
+    if (!strcmp(key, "tensor_cores")) { c->use_tc = value && c->precision != WHENET_PRECISION_FP32; return 0; }
+    if (!strcmp(key, "chunk")) {
+        if (value < 1) return fail(WHENET_EINVAL, "chunk must be >= 1");
+        c->chunk = std::min(value, c->max_batch);
+        return 0;
+    }
+    return fail(WHENET_ENOTFOUND, "unknown option %s", key);
+}
+
+void whenet_destroy(whenet_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    free_ws(c);
+    for (auto& kv : c->taps) cudaFree(kv.second.first);
+    for (auto& p : c->ev_used) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->d_arena) cudaFree(c->d_arena);
+    if (c->d_arena16) cudaFree(c->d_arena16);
+    if (c->d_angles) cudaFree(c->d_angles);
+    if (c->d_logits) cudaFree(c->d_logits);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_ready[i]) cudaEventDestroy(c->ev_ready[i]);
+        if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
+    }
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+}  // extern "C"

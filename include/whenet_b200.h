@@ -1,0 +1,133 @@
+/*
+ * whenet_b200.h - C ABI of the B200-native WHENet per-crop forward.
+ *
+ * The reference has no FFI of its own: its whole hot path is the Python class
+ * in reference whenet.py (WHENet.__init__ :7-20, WHENet.get_angle :22-34,
+ * self.model.predict :27) sitting on Keras/TensorFlow.  This header is the
+ * boundary a host in any language binds instead of Keras; each entry point
+ * cites the reference line(s) it replaces.  Plain C types only, no C++
+ * exceptions cross it.  Every function returns 0 on success or a negative
+ * WHENET_E* code; whenet_last_error() returns the message of the last failure
+ * on the calling thread.
+ *
+ * A context is bound to one device and one stream and is NOT thread-safe
+ * (the reference is single-threaded and synchronous as well: demo_video.py:49-63).
+ * Use one context per GPU / per host thread.
+ */
+#ifndef WHENET_B200_H
+#define WHENET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WHENET_OK              0
+#define WHENET_EINVAL         -1   /* bad argument (NULL, n<1, n>max_batch, wrong shape)      */
+#define WHENET_ECUDA          -2   /* a CUDA runtime/driver call failed (message has details) */
+#define WHENET_ENOWEIGHTS     -3   /* forward called before whenet_load_weights               */
+#define WHENET_ESHAPE         -4   /* a weight tensor is missing or has the wrong shape       */
+#define WHENET_ENOTFOUND      -5   /* unknown tap / kernel name                               */
+
+#define WHENET_PRECISION_FP32  0   /* fp32 storage + fp32 FMA: the parity mode                */
+#define WHENET_PRECISION_BF16  1   /* bf16 activations, fp32 accumulate: the throughput mode  */
+#define WHENET_PRECISION_FP16  2   /* fp16 activations, fp32 accumulate                       */
+
+#define WHENET_IMG        224
+#define WHENET_N_YAW      120      /* reference whenet.py:11 */
+#define WHENET_N_PITCH     66      /* reference whenet.py:12 */
+#define WHENET_N_ROLL      66      /* reference whenet.py:13 */
+#define WHENET_N_LOGITS   252
+
+typedef struct whenet_ctx whenet_ctx;
+
+/* One named float32 tensor of the Keras weights file ("conv2d_1/kernel:0", ...),
+ * row-major in the file's own layout (conv HWIO, depthwise [kh,kw,C,1], BN [C],
+ * Dense [in,out]).  Borrowed for the duration of whenet_load_weights only. */
+typedef struct {
+    const char*  name;
+    const float* data;
+    int32_t      ndim;
+    int64_t      dims[4];
+} whenet_tensor;
+
+/* Per-kernel device timings of the last profiled forward (CUDA events on the
+ * context's stream).  bytes/flops are the ALGORITHMIC figures of DESIGN.md. */
+typedef struct {
+    char   name[48];
+    float  ms;          /* summed over `launches` launches                 */
+    int    launches;
+    double bytes;       /* algorithmic HBM bytes those launches must move   */
+    double flops;       /* algorithmic flops (2*MAC) of those launches      */
+} whenet_kernel_stat;
+
+/* replaces: graph construction, reference whenet.py:8-14 (+ device choice via
+ * CUDA_VISIBLE_DEVICES, demo_video.py:79-80).  `max_batch` bounds n of one
+ * forward call (activation workspace is sized for min(max_batch, chunk)). */
+int whenet_create(whenet_ctx** out, int device, int max_batch, int precision);
+
+/* replaces: self.model.load_weights(snapshot), reference whenet.py:15-16.
+ * Takes the file's raw tensors by name; folds BatchNorm (eps 1e-3) into the
+ * preceding conv, re-lays weights out for the kernels and uploads them. */
+int whenet_load_weights(whenet_ctx* ctx, const whenet_tensor* tensors, int n_tensors);
+
+/* Run on an existing CUDA stream (cudaStream_t / CUstream) instead of the
+ * context's own; NULL restores the internal stream. */
+int whenet_set_stream(whenet_ctx* ctx, void* cuda_stream);
+
+/* replaces: WHENet.get_angle(img), reference whenet.py:22-34, for uint8 input.
+ * `nhwc_rgb`: n x 224 x 224 x 3 RGB bytes (host memory, or device memory when
+ * in_is_device != 0).  Normalisation (whenet.py:25-26) happens on the device
+ * through a 3x256 table holding float32(((v/255)-mean)/std) evaluated in
+ * float64 exactly as numpy does there.  `angles_out`: n x 3 floats
+ * (yaw, pitch, roll in degrees) ; `logits_out`: NULL or n x 252 floats
+ * (yaw 120 | pitch 66 | roll 66) = what self.model.predict returns
+ * (whenet.py:27).  Outputs go to host memory, or to device memory when
+ * out_is_device != 0 (then the call is asynchronous on the context's stream). */
+int whenet_forward_u8(whenet_ctx* ctx, const uint8_t* nhwc_rgb, int n, int in_is_device,
+                      float* angles_out, float* logits_out, int out_is_device);
+
+/* replaces: self.model.predict(img, batch_size=8), reference whenet.py:27, for
+ * an already normalised float32 n x 224 x 224 x 3 input. */
+int whenet_forward_f32(whenet_ctx* ctx, const float* nhwc_normalised, int n, int in_is_device,
+                       float* angles_out, float* logits_out, int out_is_device);
+
+/* Block until everything queued by this context has finished. */
+int whenet_synchronize(whenet_ctx* ctx);
+
+/* Pinned host memory for asynchronous input staging (optional). */
+void* whenet_host_alloc(size_t bytes);
+void  whenet_host_free(void* p);
+
+/* ---- test / measurement hooks (no reference counterpart) ---- */
+
+/* Keep float32 copies of intermediate tensors of the NEXT forwards
+ * ("stem", "dw1".."dw16", "gate1".."gate16", "block1".."block16", "head",
+ * "pooled"); only for n <= 8. */
+int whenet_debug_enable_taps(whenet_ctx* ctx, int enable);
+/* Copy a tap to host; *n_elems receives its element count (call with out=NULL to query). */
+int whenet_debug_tap(whenet_ctx* ctx, const char* name, float* out, size_t cap_elems, size_t* n_elems);
+
+/* Time every kernel of the NEXT forwards with CUDA events. */
+int whenet_profile_enable(whenet_ctx* ctx, int enable);
+/* Read (and reset) the accumulated per-kernel statistics; returns the count written. */
+int whenet_profile_read(whenet_ctx* ctx, whenet_kernel_stat* out, int cap);
+
+/* Kernels launched by this context since creation (the bench's gpu_launches). */
+int64_t whenet_launch_count(whenet_ctx* ctx);
+
+/* Select the kernel family: 0 = CUDA-core fp32-FMA kernels for everything,
+ * 1 = tcgen05 tensor-core kernels for the 1x1 convolutions where the storage
+ * type allows (bf16/fp16).  Default: 1 for bf16/fp16, 0 for fp32. */
+int whenet_set_option(whenet_ctx* ctx, const char* key, int value);
+
+const char* whenet_last_error(void);
+const char* whenet_version(void);
+void whenet_destroy(whenet_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WHENET_B200_H */
