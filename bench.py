@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py - WHENet per-crop forward throughput on B200 (see the contract in the task + DESIGN.md).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--precision bf16] [--impl ours|reference]
+
+A "step" is one pass of the hot path (reference whenet.py:22-34) over one batch of B synthetic
+224x224x3 uint8 crops per GPU (default B=512: BASELINE.json configs[2]; at N GPUs the global batch
+is N*B = configs[3] for N=8), followed - when N>1 - by the all-gather of the angles.
+
+value  : crops/s, inputs already resident in HBM, CUDA events on the launching stream, max over ranks
+e2e    : crops/s through WHENet.forward_host(): pinned host uint8 in, H2D + forward + D2H of the angles
+         inside the timed region
+roofline: dominant kernel family (per-kernel CUDA events recorded inside the library on its stream)
+cpu_baseline: the torch-CPU port of the oracle on this box's host cores, bounded sample
+--impl reference: the CPU port timed through the same surface (the reference's Keras/TF-1.12 stack
+         cannot be installed: requirements.txt:3-5 pins are Python<=3.6 era and absent offline)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ALGO_ELEMS_PER_CROP = 6_938_112      # activation elements moved by the <=2-kernels-per-block plan
+FLOP_PER_CROP = 2 * 389_533_088
+IMG_BYTES = 224 * 224 * 3
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json; sustained bf16)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port(threads=None):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from whenet_oracle import TorchCpuPort
+    import whenet_b200
+    names, w = whenet_b200.weights.load_snapshot(whenet_b200.weights.DEFAULT_NPZ)
+    return TorchCpuPort(names, w, threads=threads)
+
+
+def time_cpu(port, crops, reps):
+    port.get_angle(crops[:8])
+    ts = []
+    for _ in range(reps):
+        t = time.perf_counter()
+        port.get_angle(crops)
+        ts.append(time.perf_counter() - t)
+    return statistics.median(ts)
+
+
+def run_reference(args):
+    """The reference arm: CPU port of whenet.py:22-34 (batch_size=8 chunking) on all host cores."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    port = cpu_port(threads=cores)
+    sample = 32                                    # crops per step: a bounded sample of the B-crop batch
+    rng = np.random.default_rng(0)
+    crops = rng.integers(0, 256, (sample, 224, 224, 3), dtype=np.uint8)
+    for _ in range(max(args.warmup, 1)):
+        port.get_angle(crops)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        port.get_angle(crops)
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    line = {"impl": "reference", "metric": "head-crops/sec @224x224", "value": v, "unit": "crops/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "batch=%d synthetic 224x224x3 uint8 crops per GPU (configs[2]); CPU arm times a %d-crop "
+                                   "sample per step" % (args.batch, sample)},
+            "cpu_baseline": {"value": v, "unit": "crops/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "%d crops/step x %d steps, torch-CPU fp32 port of the oracle (Keras/TF-1.12 not installable)" % (sample, args.steps)},
+            "e2e": {"value": v, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=512, help="crops per GPU per step")
+    ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--chunk", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import whenet_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+
+    net = whenet_b200.WHENet(whenet_b200.weights.DEFAULT_NPZ, device=local, precision=args.precision, max_batch=B)
+    if args.chunk:
+        net.set_option("chunk", args.chunk)
+    stream = torch.cuda.current_stream()
+    net.set_stream(stream.cuda_stream)
+
+    # ---- synthetic inputs: NBUF different resident batches rotate so inputs are never L2-hot (NBUF*B*150 KB > 126 MB)
+    NBUF = max(2, -(-(160 << 20) // (B * IMG_BYTES)))
+    g = torch.Generator(device="cuda").manual_seed(1000 + rank)
+    dev_in = [torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8, device="cuda", generator=g) for _ in range(NBUF)]
+    angles = torch.empty((B, 3), dtype=torch.float32, device="cuda")
+    gathered = torch.empty((world * B, 3), dtype=torch.float32, device="cuda") if world > 1 else None
+
+    def step(i):
+        net.forward_device(dev_in[i % NBUF], angles)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, angles)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(W):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = net.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record(stream)
+    for i in range(K):
+        step(W + i)
+    e1.record(stream)
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = net.launch_count() - l0
+    clocks = sampler.finish() if sampler else None
+    t = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * K / (ms_max * 1e-3)
+
+    # ---- e2e: pinned host uint8 -> H2D -> forward -> D2H angles, through the public host API
+    h_in = [torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    h_out = torch.empty((B, 3), dtype=torch.float32).pin_memory()
+    KE = max(5, K // 2)
+    for i in range(3):
+        net.forward_host(h_in[i % 2], h_out)
+    sync_all()
+    e0.record(stream)
+    for i in range(KE):
+        net.forward_host(h_in[i % 2], h_out)
+        if world > 1:
+            angles.copy_(h_out, non_blocking=True)
+            dist.all_gather_into_tensor(gathered, angles)
+    e1.record(stream)
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * KE / (float(t.item()) * 1e-3)
+
+    # ---- per-kernel CUDA-event profile (recorded inside the library on the launching stream)
+    net.enable_profile(True)
+    KP = min(K, 10)
+    for i in range(KP):
+        net.forward_device(dev_in[i % NBUF], angles)
+    torch.cuda.synchronize()
+    stats = net.read_profile()
+    net.enable_profile(False)
+
+    if rank == 0:
+        pk = peaks()
+        fam = {}
+        for s in stats:
+            nm = s["name"]
+            f = "pw_conv(1x1)" if (nm.endswith(".expand") or nm.endswith(".project") or nm == "head.conv") else \
+                "dw_conv" if nm.endswith(".dw") else "se_gate" if nm.endswith(".se") else nm
+            a = fam.setdefault(f, {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "launches": 0})
+            for k in ("ms", "bytes", "flops", "launches"):
+                a[k] += s[k]
+        tot_ms = sum(a["ms"] for a in fam.values())
+        dom = max(fam.items(), key=lambda kv: kv[1]["ms"])
+        dname, d = dom
+        achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+        es = 4 if args.precision == "fp32" else 2
+        roof = {"kernel": dname, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "share_of_step": d["ms"] / tot_ms, "launches_per_step": d["launches"] / KP,
+                "ms_per_launch_avg": d["ms"] / d["launches"],
+                "tflops": d["flops"] / (d["ms"] * 1e-3) / 1e12,
+                "families": {k: {"ms_per_step": v["ms"] / KP, "GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
+                                 "TFLOPs": v["flops"] / (v["ms"] * 1e-3) / 1e12} for k, v in fam.items()},
+                "whole_net": {"algorithmic_bytes_per_crop": ALGO_ELEMS_PER_CROP * es,
+                              "achieved_GBps": ALGO_ELEMS_PER_CROP * es * value / world / 1e9,
+                              "frac_of_hbm_peak": ALGO_ELEMS_PER_CROP * es * value / world / 1e9 / pk["hbm_gbs"],
+                              "achieved_TFLOPs": FLOP_PER_CROP * value / world / 1e12}}
+        cpu = None
+        if not args.no_cpu and world == 1:
+            import torch as _t
+            port = cpu_port(threads=os.cpu_count())
+            sample = 32
+            crops = np.random.default_rng(0).integers(0, 256, (sample, 224, 224, 3), dtype=np.uint8)
+            dt = time_cpu(port, crops, 5)
+            cpu = {"value": sample / dt, "unit": "crops/s", "cores": _t.get_num_threads(), "kind": "port",
+                   "sample": "%d crops, median of 5, torch-CPU fp32 port of the oracle with the reference's batch_size=8 chunking "
+                             "(Keras/TF-1.12 not installable)" % sample}
+        line = {"metric": "head-crops/sec @224x224 %s" % args.precision, "value": value, "unit": "crops/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": "batch=%d synthetic 224x224x3 uint8 crops per GPU (BASELINE configs[2]; global batch %d%s)"
+                                       % (B, world * B, ", NCCL all-gather of angles" if world > 1 else ""),
+                           "global_batch": world * B, "parallelism": "dp%d" % world, "weights": "WHENet.h5 (converted npz)",
+                           "l2": "inputs rotate over %d resident batches (%d MB > 126 MB L2)" % (NBUF, NBUF * B * IMG_BYTES >> 20)},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": B * IMG_BYTES, "d2h_bytes_per_step": B * 12,
+                        "api": "WHENet.forward_host (pinned uint8 in, angles out)"},
+                "gpu_launches": int(launches * world),
+                "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

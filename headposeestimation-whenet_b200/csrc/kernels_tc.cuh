@@ -1,7 +1,310 @@
-// placeholder, replaced below
+// kernels_tc.cuh - tcgen05 (5th-gen tensor core) kernels for the 1x1 convolutions.
+//
+//   out[m, n] = act( bias[n] + sum_k (A[m,k] * gate[m/hw, k]) * Wt[n,k] ) (+ resid[m,n])
+//
+// A  : activations, NHWC == row-major [M = crops*H*W][K = Cin], 16-bit (bf16 / fp16)   -> "K-major"
+// Wt : BN-folded weights transposed to [N = Cout][K], 16-bit                           -> "K-major"
+// D  : fp32 accumulator in tensor memory (TMEM), 128 lanes (pixels) x n_tile columns
+//
+// One CTA owns a 128-pixel x n_tile(<=256) output tile.  The K loop runs in
+// blocks of 64 channels through a 2-stage shared-memory ring:
+//   all 128 threads : global -> registers (-> x SE gate) -> st.shared in the canonical
+//                     K-major SWIZZLE_128B UMMA layout (16-byte chunk c of row r lands at
+//                     chunk c ^ (r & 7) of its 128-byte row; 8-row atoms of 1024 B)
+//   thread 0        : tcgen05.mma.cta_group::1.kind::f16 (M=128, N=n_tile, K=16) x 4 per block,
+//                     tcgen05.commit -> mbarrier of that stage (frees the stage for the next fill)
+//   epilogue        : warp w reads TMEM lanes 32w..32w+31 with tcgen05.ld (thread == pixel row),
+//                     adds the folded BN shift, swish / residual, packs to 16 bit, 16-byte stores.
+// Several CTAs are resident per SM (smem <= 96 KB, TMEM <= 256 columns), so one CTA's
+// fills overlap another's MMAs and epilogue.
+//
+// Every mbarrier wait is bounded: a wait that exceeds its budget sets a flag in
+// global memory and the CTA bails out instead of hanging the GPU.
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
-namespace whenet { namespace tc {
+#include <stdint.h>
+
+#include "kernels_simt.cuh"
+
+namespace whenet {
+namespace tc {
+
+__device__ int g_tc_timeout_flag = 0;
+
+constexpr int BM = 128;          // pixels per CTA == TMEM lanes == UMMA M
+constexpr int BK = 64;           // channels per stage (one 128-byte swizzle row of 16-bit elements)
+constexpr int STAGES = 2;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// bounded parity wait; returns false on timeout
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t it = 0; it < (1u << 22); ++it) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    atomicExch(&g_tc_timeout_flag, 1);
+    return false;
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 = 1 | [32,46) SBO >> 4 = 64 (8 rows x 128 B)
+//   [46,48) version = 1 (Blackwell) | [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)64 << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): D=f32, A/B = bf16 or f16, both K-major.
+__host__ __device__ inline uint32_t make_idesc(bool is_bf16, int umma_n) {
+    uint32_t d = 0;
+    d |= 1u << 4;                           // c_format = F32
+    d |= (is_bf16 ? 1u : 0u) << 7;          // a_format
+    d |= (is_bf16 ? 1u : 0u) << 10;         // b_format
+    d |= (uint32_t)(umma_n >> 3) << 17;     // n_dim
+    d |= (uint32_t)(BM >> 4) << 24;         // m_dim
+    return d;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <typename T> __device__ __forceinline__ uint4 scale8(uint4 raw, const float* g);
+template <> __device__ __forceinline__ uint4 scale8<__nv_bfloat16>(uint4 raw, const float* g) {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+    const float4 g0 = *reinterpret_cast<const float4*>(g), g1 = *reinterpret_cast<const float4*>(g + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h[i]);
+        h[i] = __floats2bfloat162_rn(f.x * gg[2 * i], f.y * gg[2 * i + 1]);
+    }
+    return raw;
+}
+template <> __device__ __forceinline__ uint4 scale8<__half>(uint4 raw, const float* g) {
+    __half2* h = reinterpret_cast<__half2*>(&raw);
+    const float4 g0 = *reinterpret_cast<const float4*>(g), g1 = *reinterpret_cast<const float4*>(g + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __half22float2(h[i]);
+        h[i] = __floats2half2_rn(f.x * gg[2 * i], f.y * gg[2 * i + 1]);
+    }
+    return raw;
+}
+
+// grid = (n_tiles, m_tiles): CTAs sharing an A tile are adjacent in launch order (L2 reuse of A).
+template <typename T, bool SWISH, bool GATE, bool RESID>
+__global__ void __launch_bounds__(128) pw_tc_kernel(const T* __restrict__ A, const T* __restrict__ Wt,
+                                                    const float* __restrict__ bias, const float* __restrict__ gate,
+                                                    const T* __restrict__ resid, T* __restrict__ out,
+                                                    long long M, int K, int N, int hw,
+                                                    int n_tile,        // output columns per CTA (multiple of 8)
+                                                    int umma_n,        // n_tile rounded up to 16
+                                                    int tmem_cols,     // power of two >= umma_n, >= 32
+                                                    uint32_t idesc) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t mbar[STAGES];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ int s_abort;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // SWIZZLE_128B atoms need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int w_stage_bytes = umma_n * BK * 2;
+    uint8_t* sA = smem;                                 // [STAGES][128 rows][128 B]
+    uint8_t* sW = smem + STAGES * A_STAGE_BYTES;        // [STAGES][umma_n rows][128 B]
+
+    const long long m0 = (long long)blockIdx.y * BM;
+    const int n0 = blockIdx.x * n_tile;
+    const int n_valid = min(n_tile, N - n0);            // real output columns of this CTA
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        s_abort = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"((uint32_t)tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = s_tmem_base;
+
+    const int nkb = (K + BK - 1) / BK;
+    const int kchunks = K >> 3;                          // valid 16-byte chunks per row (K % 8 == 0)
+
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb & 1;
+        if (kb >= STAGES) {
+            // the MMAs that read this stage (block kb-2) must have completed
+            if (!mbar_wait(&mbar[s], ((kb >> 1) - 1) & 1)) s_abort = 1;
+        }
+        uint8_t* a_st = sA + s * A_STAGE_BYTES;
+        uint8_t* w_st = sW + s * w_stage_bytes;
+        const int kc0 = kb * 8;                          // first global chunk of this block
+        // ---- A tile: 128 rows x 8 chunks; thread -> (row = i*16 + tid/8, chunk = tid%8): 128 B coalesced per row
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = i * 16 + (tid >> 3), c = tid & 7;
+            const long long m = m0 + r;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (m < M && kc0 + c < kchunks) {
+                v = *reinterpret_cast<const uint4*>(A + m * K + (long long)(kc0 + c) * 8);
+                if (GATE) v = scale8<T>(v, gate + (m / hw) * K + (kc0 + c) * 8);
+            }
+            *reinterpret_cast<uint4*>(a_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
+        }
+        // ---- W tile: umma_n rows x 8 chunks (rows >= n_valid and chunks >= K/8 are zero)
+        for (int idx = tid; idx < umma_n * 8; idx += 128) {
+            const int r = idx >> 3, c = idx & 7;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (r < n_valid && kc0 + c < kchunks)
+                v = *reinterpret_cast<const uint4*>(Wt + (long long)(n0 + r) * K + (long long)(kc0 + c) * 8);
+            *reinterpret_cast<uint4*>(w_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
+        }
+        // generic-proxy writes -> visible to the async proxy (tensor core) before the MMA is issued
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0 && !s_abort) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int krem = min(BK, K - kb * BK);
+            const int ksteps = (krem + 15) >> 4;
+            const uint64_t ad = make_desc(smem_u32(a_st)), bd = make_desc(smem_u32(w_st));
+            for (int k = 0; k < ksteps; ++k)      // +32 bytes along K inside the swizzle row = +2 in the address field
+                umma_f16(tmem_d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            umma_commit(&mbar[s]);
+        }
+    }
+    // ---- wait for the last MMA group (commits complete in issue order)
+    {
+        const int last = nkb - 1;
+        if (!mbar_wait(&mbar[last & 1], (last >> 1) & 1)) s_abort = 1;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncthreads();
+
+    // ---- epilogue: thread == pixel row
+    const long long m = m0 + tid;
+    if (!s_abort) {
+        const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);
+        for (int c0 = 0; c0 < n_valid; c0 += 16) {
+            float v[16];
+            tmem_ld16(lane_base + (uint32_t)c0, v);     // warp-collective: every lane executes it
+            if (m < M) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int n = n0 + c0 + h * 8;
+                    if (c0 + h * 8 >= n_valid) break;
+                    float o[8];
+                    const float4 b0 = *reinterpret_cast<const float4*>(bias + n), b1 = *reinterpret_cast<const float4*>(bias + n + 4);
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float x = v[h * 8 + j] + bb[j];
+                        o[j] = SWISH ? swish_f(x) : x;
+                    }
+                    if (RESID) {
+                        float r[8];
+                        ld8<T>(resid + m * N + n, r);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] += r[j];
+                    }
+                    st8<T>(out + m * N + n, o);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)tmem_cols) : "memory");
+}
+
+// returns 0 = launched, >0 = shape unsupported (caller falls back to the CUDA-core kernel), <0 = error
 template <typename T>
-int launch_pw_tc(cudaStream_t, const T*, const void*, const float*, const float*, const T*, T*, long long, int, int, int, bool) { return 1; }
-}}
+int launch_pw_tc(cudaStream_t stream, const T* A, const void* Wt16, const float* bias, const float* gate, const T* resid,
+                 T* out, long long M, int K, int N, int hw, bool swish) {
+    if (sizeof(T) != 2) return 1;
+    if ((K & 7) || (N & 7)) return 1;
+    // columns per CTA: whole N when it fits 256 TMEM columns, otherwise an even split into <=256 wide tiles
+    int n_tile = N;
+    if (N > 256) {
+        int parts = (N + 255) / 256;
+        while (true) {
+            n_tile = ((N + parts - 1) / parts + 15) & ~15;
+            if (n_tile <= 256) break;
+            ++parts;
+        }
+    }
+    const int umma_n = (n_tile + 15) & ~15;
+    int tmem_cols = 32;
+    while (tmem_cols < umma_n) tmem_cols <<= 1;
+    const uint32_t idesc = make_idesc(std::is_same<T, __nv_bfloat16>::value, umma_n);
+    const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + (size_t)umma_n * BK * 2) + 1024;
+    dim3 grid((unsigned)((N + n_tile - 1) / n_tile), (unsigned)((M + BM - 1) / BM));
+    const T* W = reinterpret_cast<const T*>(Wt16);
+#define TC(SW, GA, RE)                                                                                              \
+    do {                                                                                                            \
+        auto kfn = pw_tc_kernel<T, SW, GA, RE>;                                                                     \
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) return -1; \
+        kfn<<<grid, 128, smem, stream>>>(A, W, bias, gate, resid, out, M, K, N, hw, n_tile, umma_n, tmem_cols, idesc); \
+    } while (0)
+    if (swish && !gate && !resid) TC(true, false, false);
+    else if (!swish && gate && !resid) TC(false, true, false);
+    else if (!swish && gate && resid) TC(false, true, true);
+    else if (!swish && !gate && !resid) TC(false, false, false);
+    else return 1;
+#undef TC
+    return 0;
+}
+
+inline int read_and_clear_timeout_flag() {
+    int v = 0, z = 0;
+    if (cudaMemcpyFromSymbol(&v, g_tc_timeout_flag, sizeof(int)) != cudaSuccess) return -1;
+    if (v) cudaMemcpyToSymbol(g_tc_timeout_flag, &z, sizeof(int));
+    return v;
+}
+
+}  // namespace tc
+}  // namespace whenet

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/whenet_b200.h"
@@ -92,6 +93,7 @@ struct whenet_ctx {
     int device = 0, max_batch = 0, precision = 0;
     int chunk = 0;          // crops per pass through the net
     int use_tc = 0;         // tensor-core kernels for the 1x1 convs
+    bool tc_used = false;   // a tcgen05 kernel ran since the last timeout-flag check
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     bool weights_loaded = false;
     std::vector<BlockCfg> blocks;
@@ -207,13 +209,20 @@ int ensure_ws(whenet_ctx* c) {
     if (c->ws_chunk == c->chunk && c->bufA) return 0;
     free_ws(c);
     const size_t es = esize(c->precision), ch = (size_t)c->chunk;
-    // per-crop element counts: block io <= 112*112*32, expanded <= 112*112*96, dw out <= 112*112*32
-    const size_t io = 112ull * 112 * 32, ex = 112ull * 112 * 96, dw = 112ull * 112 * 32;
+    // per-crop element counts from the block table: block io (stem out 112*112*32 is the largest),
+    // expanded tensor (block 2: 112*112*96; also holds the 7*7*1280 head features), depthwise output (block 3: 56*56*144)
+    size_t io = 112ull * 112 * 32, ex = 49ull * 1280, dw = 0, part = 0;
+    for (const BlockCfg& b : c->blocks) {
+        io = std::max(io, (size_t)b.hout * b.hout * b.cout);
+        if (b.has_expand) ex = std::max(ex, (size_t)b.hin * b.hin * b.cexp);
+        dw = std::max(dw, (size_t)b.hout * b.hout * b.cexp);
+        part = std::max(part, (size_t)((b.hout + 7) / 8) * b.cexp);
+    }
     CK(cudaMalloc(&c->bufA, ch * io * es));
     CK(cudaMalloc(&c->bufB, ch * io * es));
     CK(cudaMalloc(&c->bufE, ch * ex * es));
     CK(cudaMalloc(&c->bufD, ch * dw * es));
-    CK(cudaMalloc(&c->d_partial, ch * 16 * 1152 * sizeof(float)));   // <= 14 tiles x C (tiles*C <= 14*96.. ; 16*1152 bounds all)
+    CK(cudaMalloc(&c->d_partial, ch * part * sizeof(float)));         // [crop][<= ceil(hout/8) tiles][cexp]
     CK(cudaMalloc(&c->d_gate, ch * 1152 * sizeof(float)));
     CK(cudaMalloc(&c->d_pooled, ch * 1280 * sizeof(float)));
     for (int i = 0; i < 2; ++i) CK(cudaMalloc(&c->d_in[i], ch * kImgElems * sizeof(float)));
@@ -228,11 +237,13 @@ int launch_pw(whenet_ctx* c, const char* name, const T* A, const float* W, const
     const double bytes = (double)M * (K + N + (resid ? N : 0)) * sizeof(T);
     const double flops = 2.0 * (double)M * K * N;
     Scope sc(c, name, bytes, flops);
-    if (c->use_tc && Wt16 && sizeof(T) == 2) {
-        int rc = whenet::tc::launch_pw_tc<T>(c->stream, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish);
-        if (rc == 0) { CK(cudaGetLastError()); return 0; }
-        if (rc < 0) return fail(WHENET_ECUDA, "tensor-core 1x1 launch failed for %s (rc=%d)", name, rc);
-        // rc > 0: shape not supported by the tensor-core kernel -> CUDA-core kernel below
+    if constexpr (sizeof(T) == 2) {
+        if (c->use_tc && Wt16) {
+            int rc = whenet::tc::launch_pw_tc<T>(c->stream, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish);
+            if (rc == 0) { CK(cudaGetLastError()); c->tc_used = true; return 0; }
+            if (rc < 0) return fail(WHENET_ECUDA, "tensor-core 1x1 launch failed for %s (rc=%d)", name, rc);
+            // rc > 0: shape not supported by the tensor-core kernel -> CUDA-core kernel below
+        }
     }
     dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
 #define PW(SW, GA, RE) whenet::pw_conv_kernel<T, SW, GA, RE><<<grid, 256, 0, c->stream>>>(A, W, bias, gate, resid, out, M, K, N, hw)
@@ -367,6 +378,11 @@ int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* a
         if (logits_out)
             CK(cudaMemcpyAsync(logits_out, c->d_logits, (size_t)n * WHENET_N_LOGITS * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
+        if (c->tc_used) {
+            c->tc_used = false;
+            if (whenet::tc::read_and_clear_timeout_flag() != 0)
+                return fail(WHENET_ECUDA, "a tcgen05 kernel timed out waiting on an mbarrier (results invalid)");
+        }
     }
     return 0;
 }
@@ -417,6 +433,13 @@ bool fold_bn(const TensorMap& tm, int bn_id, int c, BnFold* out, std::string* er
     }
     return true;
 }
+
+inline void whenet_host_cvt(float v, float* o) { *o = v; }
+inline void whenet_host_cvt(float v, __nv_bfloat16* o) { *o = __float2bfloat16_rn(v); }
+inline void whenet_host_cvt(float v, __half* o) { *o = __float2half_rn(v); }
+inline float whenet_host_cvt_back(float v) { return v; }
+inline float whenet_host_cvt_back(__nv_bfloat16 v) { return __bfloat162float(v); }
+inline float whenet_host_cvt_back(__half v) { return __half2float(v); }
 
 template <typename T16> T16 to16(float v);
 template <> __nv_bfloat16 to16<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
@@ -634,6 +657,11 @@ int whenet_synchronize(whenet_ctx* c) {
     if (!c) return fail(WHENET_EINVAL, "null context");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
+    if (c->tc_used) {
+        c->tc_used = false;
+        if (whenet::tc::read_and_clear_timeout_flag() != 0)
+            return fail(WHENET_ECUDA, "a tcgen05 kernel timed out waiting on an mbarrier (results invalid)");
+    }
     return 0;
 }
 
@@ -664,6 +692,73 @@ int whenet_debug_tap(whenet_ctx* c, const char* name, float* out, size_t cap, si
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaMemcpy(out, it->second.first, it->second.second * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
+}
+
+}  // extern "C"
+
+namespace {
+template <typename T>
+int debug_conv_impl(whenet_ctx* c, int use_tc, const float* A, const float* W, const float* bias, const float* gate,
+                    const float* resid, float* out, long long M, int K, int N, int hw, int swish) {
+    std::vector<T> hA((size_t)M * K), hWt((size_t)N * K), hR(resid ? (size_t)M * N : 0), hO((size_t)M * N);
+    auto cv = [](float v) { T t; whenet_host_cvt(v, &t); return t; };
+    for (size_t i = 0; i < hA.size(); ++i) hA[i] = cv(A[i]);
+    for (int k = 0; k < K; ++k)
+        for (int n = 0; n < N; ++n) hWt[(size_t)n * K + k] = cv(W[(size_t)k * N + n]);
+    for (size_t i = 0; i < hR.size(); ++i) hR[i] = cv(resid[i]);
+    T *dA = nullptr, *dWt = nullptr, *dR = nullptr, *dO = nullptr;
+    float *dW = nullptr, *dB = nullptr, *dG = nullptr;
+    const long long ncrops = (M + hw - 1) / hw;
+    CK(cudaMalloc(&dA, hA.size() * sizeof(T)));
+    CK(cudaMalloc(&dWt, hWt.size() * sizeof(T) + 256));
+    CK(cudaMalloc(&dO, hO.size() * sizeof(T)));
+    CK(cudaMalloc(&dW, (size_t)K * N * 4));
+    CK(cudaMalloc(&dB, (size_t)N * 4));
+    CK(cudaMemcpy(dA, hA.data(), hA.size() * sizeof(T), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dWt, hWt.data(), hWt.size() * sizeof(T), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dW, W, (size_t)K * N * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
+    if (gate) { CK(cudaMalloc(&dG, (size_t)ncrops * K * 4)); CK(cudaMemcpy(dG, gate, (size_t)ncrops * K * 4, cudaMemcpyHostToDevice)); }
+    if (resid) { CK(cudaMalloc(&dR, hR.size() * sizeof(T))); CK(cudaMemcpy(dR, hR.data(), hR.size() * sizeof(T), cudaMemcpyHostToDevice)); }
+    CK(cudaMemset(dO, 0xFF, hO.size() * sizeof(T)));
+    const int saved = c->use_tc;
+    c->use_tc = use_tc;
+    int rc;
+    if (use_tc) {
+        rc = 1;
+        if constexpr (sizeof(T) == 2) rc = whenet::tc::launch_pw_tc<T>(c->stream, dA, dWt, dB, dG, dR, dO, M, K, N, hw, swish != 0);
+        if (rc == 0 && cudaGetLastError() != cudaSuccess) rc = -1;
+        if (rc != 0) rc = fail(WHENET_EINVAL, "tensor-core family cannot run M=%lld K=%d N=%d (rc=%d)", M, K, N, rc);
+        else c->tc_used = true;
+    } else {
+        rc = launch_pw<T>(c, "debug.conv1x1", dA, dW, nullptr, dB, dG, dR, dO, M, K, N, hw, swish != 0);
+    }
+    c->use_tc = saved;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (rc == 0 && e != cudaSuccess) rc = fail(WHENET_ECUDA, "debug conv failed: %s", cudaGetErrorString(e));
+    if (rc == 0 && use_tc && whenet::tc::read_and_clear_timeout_flag() != 0) rc = fail(WHENET_ECUDA, "tcgen05 kernel timed out on an mbarrier");
+    if (rc == 0) {
+        e = cudaMemcpy(hO.data(), dO, hO.size() * sizeof(T), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(WHENET_ECUDA, "copy back failed: %s", cudaGetErrorString(e));
+        else for (size_t i = 0; i < hO.size(); ++i) out[i] = whenet_host_cvt_back(hO[i]);
+    }
+    for (void* p : {(void*)dA, (void*)dWt, (void*)dR, (void*)dO, (void*)dW, (void*)dB, (void*)dG}) if (p) cudaFree(p);
+    return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int whenet_debug_conv1x1(whenet_ctx* c, int use_tc, const float* A, const float* W, const float* bias, const float* gate,
+                         const float* resid, float* out, int64_t M, int K, int N, int hw, int swish) {
+    if (!c || !A || !W || !bias || !out || M < 1 || K < 8 || N < 8 || hw < 1) return fail(WHENET_EINVAL, "bad arguments");
+    CK(cudaSetDevice(c->device));
+    switch (c->precision) {
+        case WHENET_PRECISION_FP32: return debug_conv_impl<float>(c, use_tc, A, W, bias, gate, resid, out, M, K, N, hw, swish);
+        case WHENET_PRECISION_BF16: return debug_conv_impl<__nv_bfloat16>(c, use_tc, A, W, bias, gate, resid, out, M, K, N, hw, swish);
+        case WHENET_PRECISION_FP16: return debug_conv_impl<__half>(c, use_tc, A, W, bias, gate, resid, out, M, K, N, hw, swish);
+    }
+    return fail(WHENET_EINVAL, "bad precision");
 }
 
 int whenet_profile_enable(whenet_ctx* c, int enable) {

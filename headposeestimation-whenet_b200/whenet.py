@@ -189,6 +189,19 @@ class WHENet:
         check(self._L.whenet_debug_tap(self._h, name.encode(), _ptr(out), n.value, C.byref(n)))
         return out
 
+    def debug_conv1x1(self, A, W, bias, gate=None, resid=None, hw=None, swish=False, use_tc=False):
+        """One 1x1 conv through the chosen kernel family (test hook; see whenet_debug_conv1x1)."""
+        A = np.ascontiguousarray(A, np.float32); W = np.ascontiguousarray(W, np.float32)
+        bias = np.ascontiguousarray(bias, np.float32)
+        M, K = A.shape
+        N = W.shape[1]
+        gate = None if gate is None else np.ascontiguousarray(gate, np.float32)
+        resid = None if resid is None else np.ascontiguousarray(resid, np.float32)
+        out = np.empty((M, N), np.float32)
+        check(self._L.whenet_debug_conv1x1(self._h, int(use_tc), _ptr(A), _ptr(W), _ptr(bias), _ptr(gate), _ptr(resid),
+                                           _ptr(out), M, K, N, int(hw or M), int(swish)))
+        return out
+
     def enable_profile(self, on: bool = True):
         check(self._L.whenet_profile_enable(self._h, int(on)))
 

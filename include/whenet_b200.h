@@ -110,6 +110,14 @@ int whenet_debug_enable_taps(whenet_ctx* ctx, int enable);
 /* Copy a tap to host; *n_elems receives its element count (call with out=NULL to query). */
 int whenet_debug_tap(whenet_ctx* ctx, const char* name, float* out, size_t cap_elems, size_t* n_elems);
 
+/* Run ONE 1x1 convolution through the kernel family chosen by use_tc (0 CUDA-core, 1 tcgen05):
+ * out[m,n] = act(bias[n] + sum_k A[m,k]*gate[m/hw,k]*W[k,n]) (+ resid[m,n]).  All arrays are host
+ * float32 (converted to the context's storage type on the way in and back on the way out);
+ * gate / resid may be NULL.  Returns WHENET_EINVAL when the family cannot run the shape. */
+int whenet_debug_conv1x1(whenet_ctx* ctx, int use_tc, const float* A, const float* W, const float* bias,
+                         const float* gate, const float* resid, float* out,
+                         int64_t M, int K, int N, int hw, int swish);
+
 /* Time every kernel of the NEXT forwards with CUDA events. */
 int whenet_profile_enable(whenet_ctx* ctx, int enable);
 /* Read (and reset) the accumulated per-kernel statistics; returns the count written. */

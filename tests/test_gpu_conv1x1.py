@@ -1,0 +1,77 @@
+"""The 1x1-convolution kernels alone, every (K, N) pair of the network, both kernel families.
+
+Reference for both families: numpy float64 on the SAME 16-bit-rounded inputs, so the only
+differences are fp32 accumulation order and the final rounding to the storage type."""
+import numpy as np
+import pytest
+
+from conftest import SNAP
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16_round(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def _layer_shapes():
+    from whenet_b200 import arch
+    shapes = set()
+    for b in arch.blocks():
+        if b.has_expand:
+            shapes.add((b.cin, b.cexp, "expand"))
+        shapes.add((b.cexp, b.cout, "project_res" if b.skip else "project"))
+    shapes.add((320, 1280, "expand"))
+    return sorted(shapes)
+
+
+@pytest.fixture(scope="module")
+def net():
+    import whenet_b200
+    m = whenet_b200.WHENet(SNAP, device=0, precision="bf16", max_batch=8)
+    yield m
+    m.close()
+
+
+@pytest.mark.parametrize("use_tc", [0, 1])
+@pytest.mark.parametrize("K,N,kind", _layer_shapes())
+def test_conv1x1_shapes(net, use_tc, K, N, kind):
+    rng = np.random.default_rng(K * 1000 + N)
+    hw = 49
+    M = 5 * hw + 17            # ragged: not a multiple of 128 nor of hw
+    A = _bf16_round(rng.standard_normal((M, K)))
+    W = _bf16_round(rng.standard_normal((K, N)) / np.sqrt(K))
+    bias = rng.standard_normal(N).astype(np.float32)
+    gate = resid = None
+    swish = kind == "expand"
+    if kind.startswith("project"):
+        gate = rng.uniform(0.1, 1.0, ((M + hw - 1) // hw, K)).astype(np.float32)
+    if kind == "project_res":
+        resid = _bf16_round(rng.standard_normal((M, N)))
+    got = net.debug_conv1x1(A, W, bias, gate=gate, resid=resid, hw=hw, swish=swish, use_tc=bool(use_tc))
+    Ag = A.astype(np.float64)
+    if gate is not None:
+        Ag = Ag * np.repeat(gate, hw, axis=0)[:M]
+        if use_tc:
+            Ag = _bf16_round(Ag).astype(np.float64)   # the tensor-core path rounds A*gate back to bf16 in smem
+    ref = Ag @ W.astype(np.float64) + bias
+    if swish:
+        ref = ref / (1.0 + np.exp(-ref))
+    if resid is not None:
+        ref = ref + resid
+    err = np.abs(got - ref)
+    tol = 2.0 ** -7 * np.abs(ref) + 2e-2          # one bf16 rounding of the output (2^-8 rel) + accumulation noise
+    assert np.all(err <= tol), (K, N, kind, float(err.max()), int(np.argmax(err - tol)))
+
+
+@pytest.mark.parametrize("M", [1, 127, 128, 129, 1000])
+def test_conv1x1_tc_row_tails(net, M):
+    rng = np.random.default_rng(M)
+    K, N = 96, 24
+    A = _bf16_round(rng.standard_normal((M, K)))
+    W = _bf16_round(rng.standard_normal((K, N)) / np.sqrt(K))
+    bias = np.zeros(N, np.float32)
+    a = net.debug_conv1x1(A, W, bias, use_tc=True)
+    b = net.debug_conv1x1(A, W, bias, use_tc=False)
+    assert np.abs(a - b).max() <= 2.0 ** -6 * max(1.0, np.abs(b).max())
