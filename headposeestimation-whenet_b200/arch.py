@@ -207,9 +207,10 @@ def macs_per_crop() -> Dict[str, int]:
         if b.has_expand:
             m["expand"] += b.hin * b.hin * b.cin * b.cexp
         m["dw"] += b.hout * b.hout * b.k * b.k * b.cexp
-        m["se"] += 2 * b.cexp * b.cse
+        # squeeze (mean over H,W) + two FCs + the gate multiply over H,W
+        m["se"] += 2 * b.cexp * b.cse + 2 * b.hout * b.hout * b.cexp
         m["project"] += b.hout * b.hout * b.cexp * b.cout
-    m["head"] = 49 * 320 * HEAD_C
+    m["head"] = 49 * 320 * HEAD_C + 49 * HEAD_C     # 1x1 conv + global average pool
     m["fc"] = HEAD_C * N_LOGITS
     m["total"] = sum(m.values())
     return m
