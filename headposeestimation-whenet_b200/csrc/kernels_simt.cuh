@@ -308,6 +308,108 @@ __global__ void __launch_bounds__(256) dw_conv_kernel(const T* __restrict__ in, 
     }
 }
 
+// ----------------------------------------------------------------------------- depthwise, register-blocked
+// Same contract as dw_conv_kernel, but every thread produces a strip of R consecutive output pixels of
+// one row for its 8 channels: the (R-1)*S+KS input columns of each kernel row are loaded once and feed
+// all the taps that touch them (KS*KS loads per output -> ((R-1)*S+KS)*KS/R), the KS weights of the
+// current kernel row live in registers.  FAST selects the 1-MUFU swish (tanh.approx) of the 16-bit modes.
+__device__ __forceinline__ float swish_fast(float x) {
+    // x*sigmoid(x) = h + h*tanh(h), h = x/2  (MUFU.TANH: one SFU op instead of EX2 + RCP)
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+
+template <typename T, int KS, int S, int R, bool FAST>
+__global__ void __launch_bounds__(256) dw_strip_kernel(const T* __restrict__ in, const float* __restrict__ w,  // [KS*KS][C]
+                                                       const float* __restrict__ bias, T* __restrict__ out,
+                                                       float* __restrict__ partial,  // [N][tiles][C]
+                                                       int Hin, int Ho, int C, int pad, int rows) {
+    extern __shared__ float s_red[];   // [PY][C]
+    constexpr int NCOL = (R - 1) * S + KS;
+    const int cv = threadIdx.x, py = threadIdx.y, PY = blockDim.y;
+    const int c0 = cv * 8;
+    const int n = blockIdx.y, tile = blockIdx.x;
+    const int r0 = tile * rows;
+    const int r1 = min(Ho, r0 + rows);
+    const int spr = (Ho + R - 1) / R;              // strips per output row
+    const int nstrips = (r1 - r0) * spr;
+    const T* in_n = in + (long long)n * Hin * Hin * C;
+    T* out_n = out + (long long)n * Ho * Ho * C;
+    float bb[8];
+    {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + c0), b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
+        bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+    }
+    float sum[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum[i] = 0.f;
+    for (int sidx = py; sidx < nstrips; sidx += PY) {
+        const int oy = r0 + sidx / spr, ox0 = (sidx % spr) * R;
+        float acc[R][8];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[r][i] = bb[i];
+        const int ix0 = ox0 * S - pad;
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky) {
+            const int iy = oy * S + ky - pad;
+            if (iy < 0 || iy >= Hin) continue;
+            float wr[KS][8];
+#pragma unroll
+            for (int kx = 0; kx < KS; ++kx) {
+                const float4 w0 = *reinterpret_cast<const float4*>(w + (ky * KS + kx) * C + c0);
+                const float4 w1 = *reinterpret_cast<const float4*>(w + (ky * KS + kx) * C + c0 + 4);
+                wr[kx][0] = w0.x; wr[kx][1] = w0.y; wr[kx][2] = w0.z; wr[kx][3] = w0.w;
+                wr[kx][4] = w1.x; wr[kx][5] = w1.y; wr[kx][6] = w1.z; wr[kx][7] = w1.w;
+            }
+            const T* row = in_n + (long long)iy * Hin * C + c0;
+#pragma unroll
+            for (int col = 0; col < NCOL; ++col) {
+                const int ix = ix0 + col;
+                if (ix < 0 || ix >= Hin) continue;
+                float x[8];
+                ld8<T>(row + (long long)ix * C, x);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int kx = col - r * S;          // compile-time after unrolling
+                    if (kx >= 0 && kx < KS) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[r][i] = fmaf(x[i], wr[kx][i], acc[r][i]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int ox = ox0 + r;
+            if (ox < Ho) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[r][i] = FAST ? swish_fast(acc[r][i]) : swish_f(acc[r][i]);
+                st8<T>(out_n + ((long long)oy * Ho + ox) * C + c0, acc[r]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sum[i] += Store<T>::rnd(acc[r][i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_red[py * C + c0 + i] = sum[i];
+    __syncthreads();
+    if (py == 0) {
+        float tot[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot[i] = 0.f;
+        for (int y = 0; y < PY; ++y)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tot[i] += s_red[y * C + c0 + i];
+        float* dst = partial + ((long long)n * gridDim.x + tile) * C + c0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[i] = tot[i];
+    }
+}
+
 // ----------------------------------------------------------------------------- SE gate
 // mean[c] = sum_tiles partial / (Ho*Ho); h = swish(W1^T mean + b1); gate = sigmoid(W2^T h + b2)
 __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ partial, int tiles, float inv_hw,

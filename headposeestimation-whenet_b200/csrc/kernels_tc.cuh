@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(128) pw_tc_kernel(const T* __restrict__ A, con
                                                     int n_tile,        // output columns per CTA (multiple of 8)
                                                     int umma_n,        // n_tile rounded up to 16
                                                     int tmem_cols,     // power of two >= umma_n, >= 32
+                                                    int n_stages,      // 1 when K <= 64 (single k-block), else 2
                                                     uint32_t idesc) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mbar[STAGES];
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(128) pw_tc_kernel(const T* __restrict__ A, con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int w_stage_bytes = umma_n * BK * 2;
     uint8_t* sA = smem;                                 // [STAGES][128 rows][128 B]
-    uint8_t* sW = smem + STAGES * A_STAGE_BYTES;        // [STAGES][umma_n rows][128 B]
+    uint8_t* sW = smem + n_stages * A_STAGE_BYTES;      // [n_stages][umma_n rows][128 B]
 
     const long long m0 = (long long)blockIdx.y * BM;
     const int n0 = blockIdx.x * n_tile;
@@ -182,23 +183,28 @@ __global__ void __launch_bounds__(128) pw_tc_kernel(const T* __restrict__ A, con
         uint8_t* a_st = sA + s * A_STAGE_BYTES;
         uint8_t* w_st = sW + s * w_stage_bytes;
         const int kc0 = kb * 8;                          // first global chunk of this block
-        // ---- A tile: 128 rows x 8 chunks; thread -> (row = i*16 + tid/8, chunk = tid%8): 128 B coalesced per row
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = i * 16 + (tid >> 3), c = tid & 7;
-            const long long m = m0 + r;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (m < M && kc0 + c < kchunks) {
-                v = *reinterpret_cast<const uint4*>(A + m * K + (long long)(kc0 + c) * 8);
-                if (GATE) v = scale8<T>(v, gate + (m / hw) * K + (kc0 + c) * 8);
+        // ---- A tile: 128 rows x cb valid 16-byte chunks (cb = 8 except in the last block), flat mapping so no
+        //      thread idles on thin layers; one extra zero chunk when cb is odd (the last k-step reads 2 chunks)
+        {
+            const int cb = min(8, kchunks - kc0);
+            const int cbp = (cb + 1) & ~1;
+            for (int idx = tid; idx < BM * cbp; idx += 128) {
+                const int r = idx / cbp, c = idx - r * cbp;
+                const long long m = m0 + r;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (m < M && c < cb) {
+                    v = *reinterpret_cast<const uint4*>(A + m * K + (long long)(kc0 + c) * 8);
+                    if (GATE) v = scale8<T>(v, gate + (m / hw) * K + (kc0 + c) * 8);
+                }
+                *reinterpret_cast<uint4*>(a_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
             }
-            *reinterpret_cast<uint4*>(a_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
         }
         // ---- W tile: umma_n rows x 8 chunks (rows >= n_valid and chunks >= K/8 are zero)
-        for (int idx = tid; idx < umma_n * 8; idx += 128) {
-            const int r = idx >> 3, c = idx & 7;
+        const int wcb = min(8, kchunks - kc0), wcbp = (wcb + 1) & ~1;
+        for (int idx = tid; idx < umma_n * wcbp; idx += 128) {
+            const int r = idx / wcbp, c = idx - r * wcbp;
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (r < n_valid && kc0 + c < kchunks)
+            if (r < n_valid && c < wcb)
                 v = *reinterpret_cast<const uint4*>(Wt + (long long)(n0 + r) * K + (long long)(kc0 + c) * 8);
             *reinterpret_cast<uint4*>(w_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
         }
@@ -224,35 +230,45 @@ __global__ void __launch_bounds__(128) pw_tc_kernel(const T* __restrict__ A, con
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();
 
-    // ---- epilogue: thread == pixel row
+    // ---- epilogue: thread == pixel row.  TMEM -> registers -> (+shift, swish, +residual) -> 16-bit -> the now idle
+    //      operand stages (row pitch odd in 16-byte units: conflict-free) -> flat, fully coalesced 16-byte global stores
     const long long m = m0 + tid;
+    const int nch = n_valid >> 3;                        // 16-byte chunks per output row
+    const int pitch16 = nch | 1;
+    uint4* stage = reinterpret_cast<uint4*>(smem);
     if (!s_abort) {
         const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);
         for (int c0 = 0; c0 < n_valid; c0 += 16) {
             float v[16];
             tmem_ld16(lane_base + (uint32_t)c0, v);     // warp-collective: every lane executes it
-            if (m < M) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int n = n0 + c0 + h * 8;
-                    if (c0 + h * 8 >= n_valid) break;
-                    float o[8];
-                    const float4 b0 = *reinterpret_cast<const float4*>(bias + n), b1 = *reinterpret_cast<const float4*>(bias + n + 4);
-                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            for (int h = 0; h < 2; ++h) {
+                const int n = n0 + c0 + h * 8;
+                if (c0 + h * 8 >= n_valid) break;
+                float o[8];
+                const float4 b0 = *reinterpret_cast<const float4*>(bias + n), b1 = *reinterpret_cast<const float4*>(bias + n + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float x = v[h * 8 + j] + bb[j];
-                        o[j] = SWISH ? swish_f(x) : x;
-                    }
-                    if (RESID) {
-                        float r[8];
-                        ld8<T>(resid + m * N + n, r);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) o[j] += r[j];
-                    }
-                    st8<T>(out + m * N + n, o);
+                for (int j = 0; j < 8; ++j) {
+                    const float x = v[h * 8 + j] + bb[j];
+                    o[j] = SWISH ? swish_fast(x) : x;
                 }
+                if (RESID && m < M) {
+                    float r[8];
+                    ld8<T>(resid + m * N + n, r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] += r[j];
+                }
+                st8<T>(reinterpret_cast<T*>(stage + tid * pitch16 + ((c0 >> 3) + h)), o);
             }
+        }
+    }
+    __syncthreads();
+    if (!s_abort) {
+        const int rows_valid = (int)min((long long)BM, M - m0);
+        for (int idx = tid; idx < rows_valid * nch; idx += 128) {
+            const int r = idx / nch, j = idx - r * nch;
+            *reinterpret_cast<uint4*>(out + (m0 + r) * N + n0 + j * 8) = stage[r * pitch16 + j];
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -281,14 +297,18 @@ int launch_pw_tc(cudaStream_t stream, const T* A, const void* Wt16, const float*
     int tmem_cols = 32;
     while (tmem_cols < umma_n) tmem_cols <<= 1;
     const uint32_t idesc = make_idesc(std::is_same<T, __nv_bfloat16>::value, umma_n);
-    const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + (size_t)umma_n * BK * 2) + 1024;
+    const int n_stages = K > BK ? STAGES : 1;
+    // operand stages, reused afterwards as the output staging tile (128 rows x odd pitch in 16-byte units)
+    const size_t stage_bytes = (size_t)n_stages * (A_STAGE_BYTES + (size_t)umma_n * BK * 2);
+    const size_t out_bytes = (size_t)BM * ((size_t)(n_tile >> 3) | 1) * 16;
+    const size_t smem = (stage_bytes > out_bytes ? stage_bytes : out_bytes) + 1024;
     dim3 grid((unsigned)((N + n_tile - 1) / n_tile), (unsigned)((M + BM - 1) / BM));
     const T* W = reinterpret_cast<const T*>(Wt16);
 #define TC(SW, GA, RE)                                                                                              \
     do {                                                                                                            \
         auto kfn = pw_tc_kernel<T, SW, GA, RE>;                                                                     \
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) return -1; \
-        kfn<<<grid, 128, smem, stream>>>(A, W, bias, gate, resid, out, M, K, N, hw, n_tile, umma_n, tmem_cols, idesc); \
+        kfn<<<grid, 128, smem, stream>>>(A, W, bias, gate, resid, out, M, K, N, hw, n_tile, umma_n, tmem_cols, n_stages, idesc); \
     } while (0)
     if (swish && !gate && !resid) TC(true, false, false);
     else if (!swish && gate && !resid) TC(false, true, false);

@@ -94,6 +94,7 @@ struct whenet_ctx {
     int chunk = 0;          // crops per pass through the net
     int use_tc = 0;         // tensor-core kernels for the 1x1 convs
     bool tc_used = false;   // a tcgen05 kernel ran since the last timeout-flag check
+    int dw_variant = 1;     // 0 = one output per thread, 1 = register-blocked strips
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     bool weights_loaded = false;
     std::vector<BlockCfg> blocks;
@@ -270,11 +271,22 @@ int launch_dw(whenet_ctx* c, const char* name, const BlockCfg& b, const BlockW& 
     const double flops = 2.0 * nb * (double)b.hout * b.hout * b.k * b.k * b.cexp;
     Scope sc(c, name, bytes, flops);
 #define DW(KS, S) whenet::dw_conv_kernel<T, KS, S><<<grid, block, smem, c->stream>>>(in, w.w_dw, w.b_dw, out, c->d_partial, b.hin, b.hout, b.cexp, b.pad, rows)
-    if (b.k == 3 && b.s == 1) DW(3, 1);
-    else if (b.k == 3 && b.s == 2) DW(3, 2);
-    else if (b.k == 5 && b.s == 1) DW(5, 1);
-    else if (b.k == 5 && b.s == 2) DW(5, 2);
-    else return fail(WHENET_EINVAL, "unsupported depthwise config");
+#define DWS(KS, S, R) whenet::dw_strip_kernel<T, KS, S, R, (sizeof(T) == 2)><<<grid, block, smem, c->stream>>>(in, w.w_dw, w.b_dw, out, c->d_partial, b.hin, b.hout, b.cexp, b.pad, rows)
+    if (c->dw_variant == 0) {
+        if (b.k == 3 && b.s == 1) DW(3, 1);
+        else if (b.k == 3 && b.s == 2) DW(3, 2);
+        else if (b.k == 5 && b.s == 1) DW(5, 1);
+        else if (b.k == 5 && b.s == 2) DW(5, 2);
+        else return fail(WHENET_EINVAL, "unsupported depthwise config");
+    } else {
+        // strip length: 4 outputs where the row is long enough, 7 = a whole row at the 7x7 / 14x14 stages
+        if (b.k == 3 && b.s == 1) { if (b.hout % 4 == 0) DWS(3, 1, 4); else DWS(3, 1, 7); }
+        else if (b.k == 3 && b.s == 2) { if (b.hout % 4 == 0) DWS(3, 2, 4); else DWS(3, 2, 7); }
+        else if (b.k == 5 && b.s == 1) { if (b.hout % 4 == 0) DWS(5, 1, 4); else DWS(5, 1, 7); }
+        else if (b.k == 5 && b.s == 2) { if (b.hout % 4 == 0) DWS(5, 2, 4); else DWS(5, 2, 7); }
+        else return fail(WHENET_EINVAL, "unsupported depthwise config");
+    }
+#undef DWS
 #undef DW
     CK(cudaGetLastError());
     return 0;
@@ -796,6 +808,7 @@ int64_t whenet_launch_count(whenet_ctx* c) { return c ? c->launches : 0; }
 int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!c || !key) return fail(WHENET_EINVAL, "bad arguments");
     if (!strcmp(key, "tensor_cores")) { c->use_tc = value && c->precision != WHENET_PRECISION_FP32; return 0; }
+    if (!strcmp(key, "dw_variant")) { c->dw_variant = value; return 0; }
     if (!strcmp(key, "chunk")) {
         if (value < 1) return fail(WHENET_EINVAL, "chunk must be >= 1");
         c->chunk = std::min(value, c->max_batch);

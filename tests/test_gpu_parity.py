@@ -147,6 +147,25 @@ def test_batch_invariance(net32, net16, sample_crops, jitter_crops):
             assert np.array_equal(one[0], full[i]), (m.precision, i)
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_dw_variants_agree(prec, sample_crops, jitter_crops):
+    """One-output-per-thread and register-blocked depthwise kernels: same taps in the same order -> same sums
+    (fp32: bitwise; 16-bit: the strip kernel uses the tanh-form swish, so only to rounding noise)."""
+    import whenet_b200
+    crops = np.concatenate([sample_crops, jitter_crops])
+    out = []
+    for v in (0, 1):
+        m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=8)
+        m.set_option("dw_variant", v)
+        m.set_option("tensor_cores", 0)
+        out.append(np.stack(m.get_angle(crops), axis=1))
+        m.close()
+    if prec == "fp32":
+        assert np.abs(out[0] - out[1]).max() < 1e-3
+    else:
+        assert np.abs(out[0] - out[1]).max() < 1.0
+
+
 def test_chunking_invariance(sample_crops, jitter_crops):
     import whenet_b200
     crops = np.concatenate([sample_crops, jitter_crops] * 3)   # 24
@@ -159,10 +178,11 @@ def test_chunking_invariance(sample_crops, jitter_crops):
 
 
 def test_more_than_max_batch(net32, sample_crops):
-    crops = np.repeat(sample_crops, 40, axis=0)   # 80 > max_batch 64
+    crops = np.tile(sample_crops, (40, 1, 1, 1))   # 80 > max_batch 64, alternating crop 0 / crop 1
     yaw, _p, _r = net32.get_angle(crops)
     assert yaw.shape == (80,)
     assert np.array_equal(yaw[0::2], np.full(40, yaw[0], dtype=np.float32))
+    assert np.array_equal(yaw[1::2], np.full(40, yaw[1], dtype=np.float32))
 
 
 def test_random_init_parity():
