@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(128) pw_tc_kernel(const T* __restrict__ A, con
                 uint4 v = make_uint4(0u, 0u, 0u, 0u);
                 if (m < M && c < cb) {
                     v = *reinterpret_cast<const uint4*>(A + m * K + (long long)(kc0 + c) * 8);
-                    if (GATE) v = scale8<T>(v, gate + (m / hw) * K + (kc0 + c) * 8);
+                    if (GATE) v = scale8<T>(v, gate + (long long)((int)m / hw) * K + (kc0 + c) * 8);   // 32-bit divide (M < 2^31)
                 }
                 *reinterpret_cast<uint4*>(a_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
             }
@@ -282,7 +282,7 @@ template <typename T>
 int launch_pw_tc(cudaStream_t stream, const T* A, const void* Wt16, const float* bias, const float* gate, const T* resid,
                  T* out, long long M, int K, int N, int hw, bool swish) {
     if (sizeof(T) != 2) return 1;
-    if ((K & 7) || (N & 7)) return 1;
+    if ((K & 7) || (N & 7) || M > 0x7fffffffLL) return 1;
     // columns per CTA: whole N when it fits 256 TMEM columns, otherwise an even split into <=256 wide tiles
     int n_tile = N;
     if (N > 256) {

@@ -18,6 +18,7 @@
 #include "../../include/whenet_b200.h"
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_fused.cuh"
 
 namespace {
 
@@ -84,6 +85,7 @@ struct BlockW {   // device pointers into the fp32 arena
     void *wt_exp = nullptr, *wt_proj = nullptr;   // 16-bit [N][K] copies for the tensor-core path
 };
 
+struct K1Plan { bool valid = false; whenet::fused::K1Params p{}; int R = 0; size_t smem = 0; };
 struct EvPair { cudaEvent_t a, b; int stat; };
 struct Stat { std::string name; double bytes = 0, flops = 0; int launches = 0; float ms = 0; };
 
@@ -95,6 +97,9 @@ struct whenet_ctx {
     int use_tc = 0;         // tensor-core kernels for the 1x1 convs
     bool tc_used = false;   // a tcgen05 kernel ran since the last timeout-flag check
     int dw_variant = 1;     // 0 = one output per thread, 1 = register-blocked strips
+    int use_fused = 0;      // K1: expand + depthwise in one kernel (16-bit storage only)
+    int fused_max_block = 6;   // blocks 2..fused_max_block use K1
+    std::vector<K1Plan> k1;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     bool weights_loaded = false;
     std::vector<BlockCfg> blocks;
@@ -219,6 +224,8 @@ int ensure_ws(whenet_ctx* c) {
         dw = std::max(dw, (size_t)b.hout * b.hout * b.cexp);
         part = std::max(part, (size_t)((b.hout + 7) / 8) * b.cexp);
     }
+    for (const K1Plan& pl : c->k1)
+        if (pl.valid) part = std::max(part, (size_t)pl.p.tiles_x * pl.p.tiles_y * pl.p.Cexp);
     CK(cudaMalloc(&c->bufA, ch * io * es));
     CK(cudaMalloc(&c->bufB, ch * io * es));
     CK(cudaMalloc(&c->bufE, ch * ex * es));
@@ -311,6 +318,24 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
         const BlockCfg& b = c->blocks[i];
         const BlockW& w = c->bw[i];
         const T* dw_in = cur;
+        int tiles = 0;
+        bool did_k1 = false;
+        if constexpr (sizeof(T) == 2) {
+            if (c->use_fused && c->k1[i].valid && b.idx <= c->fused_max_block) {
+                whenet::fused::K1Params p = c->k1[i].p;
+                p.in = cur; p.wt = w.wt_exp; p.b_exp = w.b_exp; p.w_dw = w.w_dw; p.b_dw = w.b_dw; p.out = D; p.partial = c->d_partial;
+                snprintf(nm, sizeof nm, "b%02d.k1", b.idx);
+                Scope sc(c, nm, (double)nb * ((double)b.hin * b.hin * b.cin + (double)b.hout * b.hout * b.cexp) * sizeof(T),
+                         2.0 * nb * ((double)b.hin * b.hin * b.cin * b.cexp + (double)b.hout * b.hout * b.k * b.k * b.cexp));
+                int rc = whenet::fused::launch_k1<T>(c->stream, p, b.k, b.s, c->k1[i].R, c->k1[i].smem, nb);
+                if (rc != 0) return fail(WHENET_ECUDA, "K1 launch failed for block %d (rc=%d)", b.idx, rc);
+                CK(cudaGetLastError());
+                c->tc_used = true;
+                tiles = p.tiles_x * p.tiles_y;
+                did_k1 = true;
+            }
+        }
+        if (!did_k1) {
         if (b.has_expand) {
             snprintf(nm, sizeof nm, "b%02d.expand", b.idx);
             int rc = launch_pw<T>(c, nm, cur, w.w_exp, w.wt_exp, w.b_exp, nullptr, nullptr, E,
@@ -318,10 +343,11 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
             if (rc) return rc;
             dw_in = E;
         }
-        int tiles = 0;
         snprintf(nm, sizeof nm, "b%02d.dw", b.idx);
         int rc = launch_dw<T>(c, nm, b, w, dw_in, D, nb, &tiles);
         if (rc) return rc;
+        }
+        int rc = 0;
         {
             snprintf(nm, sizeof nm, "b%02d.se", b.idx);
             Scope sc(c, nm, (double)nb * (tiles + 1) * b.cexp * 4.0, 4.0 * nb * b.cexp * b.cse);
@@ -490,6 +516,16 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
     if (const char* e2 = getenv("WHENET_TC")) c->use_tc = atoi(e2) && precision != WHENET_PRECISION_FP32;
     c->blocks = make_blocks();
     c->bw.resize(c->blocks.size());
+    c->k1.resize(c->blocks.size());
+    if (precision != WHENET_PRECISION_FP32)
+        for (size_t i = 0; i < c->blocks.size(); ++i) {
+            const BlockCfg& b = c->blocks[i];
+            if (!b.has_expand) continue;
+            K1Plan& pl = c->k1[i];
+            pl.valid = whenet::fused::plan_k1(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, precision == WHENET_PRECISION_BF16,
+                                              &pl.p, &pl.R, &pl.smem);
+        }
+    if (const char* e3 = getenv("WHENET_FUSED")) c->use_fused = atoi(e3);
     CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
@@ -809,6 +845,8 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!c || !key) return fail(WHENET_EINVAL, "bad arguments");
     if (!strcmp(key, "tensor_cores")) { c->use_tc = value && c->precision != WHENET_PRECISION_FP32; return 0; }
     if (!strcmp(key, "dw_variant")) { c->dw_variant = value; return 0; }
+    if (!strcmp(key, "fused")) { c->use_fused = value && c->precision != WHENET_PRECISION_FP32; return 0; }
+    if (!strcmp(key, "fused_max_block")) { c->fused_max_block = value; return 0; }
     if (!strcmp(key, "chunk")) {
         if (value < 1) return fail(WHENET_EINVAL, "chunk must be >= 1");
         c->chunk = std::min(value, c->max_batch);

@@ -171,7 +171,13 @@ class WHENet:
         check(self._L.whenet_forward_u8(self._h, _ptr(crops_u8), n, 0, _ptr(angles_out), _ptr(logits_out), 0))
 
     def set_stream(self, stream_ptr: Optional[int]):
-        check(self._L.whenet_set_stream(self._h, C.c_void_p(stream_ptr) if stream_ptr else None))
+        """Run on a caller-owned CUDA stream.  ``0`` (torch's default stream) is passed as
+        cudaStreamLegacy (handle 0x1) because a NULL handle means "back to the internal stream";
+        ``None`` restores the internal stream."""
+        if stream_ptr is None:
+            check(self._L.whenet_set_stream(self._h, None))
+        else:
+            check(self._L.whenet_set_stream(self._h, C.c_void_p(stream_ptr if stream_ptr else 1)))
 
     def synchronize(self):
         check(self._L.whenet_synchronize(self._h))

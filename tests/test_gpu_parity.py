@@ -124,6 +124,44 @@ def test_bf16_taps_vs_oracle(tc, oracle32, sample_crops):
     m.close()
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_fused_k1_taps(prec, oracle32, sample_crops):
+    """K1 (expand + depthwise fused, expanded tensor kept in shared memory) for every block that has an
+    expand conv: depthwise outputs, SE gates and block outputs against the oracle."""
+    import whenet_b200
+    m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=8)
+    m.set_option("fused", 1)
+    m.set_option("fused_max_block", 16)
+    taps = {}
+    oracle32.get_angle(sample_crops, taps)
+    m.enable_taps(True)
+    got = np.stack(m.get_angle(sample_crops), axis=1)
+    lim = 0.06 if prec == "bf16" else 0.01
+    for i in range(1, 17):
+        for kind in ("dw", "gate", "block"):
+            nm = "%s%d" % (kind, i)
+            ref = taps[nm].astype(np.float64).reshape(-1)
+            g = m.tap(nm).astype(np.float64)
+            e = float(np.sqrt(((g - ref) ** 2).mean()) / (np.sqrt((ref ** 2).mean()) + 1e-30))
+            assert e < lim, (nm, e)
+    ref_ang = np.stack(oracle32.get_angle(sample_crops), axis=1)
+    assert np.abs(got - ref_ang).max() < (1.5 if prec == "bf16" else 0.15)
+    m.close()
+
+
+def test_fused_k1_batch_invariance(sample_crops, jitter_crops):
+    import whenet_b200
+    crops = np.concatenate([sample_crops, jitter_crops] * 3)[:19]
+    m = whenet_b200.WHENet(SNAP, device=0, precision="bf16", max_batch=32)
+    m.set_option("fused", 1)
+    m.set_option("fused_max_block", 16)
+    full = np.stack(m.get_angle(crops), axis=1)
+    for i in (0, 7, 18):
+        one = np.stack(m.get_angle(crops[i:i + 1]), axis=1)
+        assert np.array_equal(one[0], full[i])
+    m.close()
+
+
 def test_tensor_core_path_matches_simt(sample_crops, jitter_crops):
     """Same storage type, two kernel families: results agree to bf16 rounding noise."""
     import whenet_b200

@@ -9,7 +9,7 @@ GOLD = os.path.join(ROOT, "tests", "golden"); SNAP = os.path.join(GOLD, "whenet_
 crops = np.load(os.path.join(GOLD, "sample_crops.npy"))
 o = load_oracle(SNAP, np.float32); taps = {}
 ref = np.stack(o.get_angle(crops, taps), axis=1)
-for prec in ("fp32", "bf16", "fp16"):
+for prec in os.environ.get("PRECS", "fp32,bf16,fp16").split(","):
     for tc in ((0,) if prec == "fp32" else (0, 1)):
         m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=512)
         m.set_option("tensor_cores", tc)
