@@ -110,6 +110,14 @@ template <> __device__ __forceinline__ void st8<__half>(__half* p, const float (
 // x * sigmoid(x).  expf (not __expf): the parity mode has to stay within 1e-2 deg.
 __device__ __forceinline__ float swish_f(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// x*sigmoid(x) = h + h*tanh(h), h = x/2  (MUFU.TANH: one SFU op instead of EX2 + RCP); 16-bit modes only
+__device__ __forceinline__ float swish_fast(float x) {
+    // x*sigmoid(x) = h + h*tanh(h), h = x/2  (MUFU.TANH: one SFU op instead of EX2 + RCP)
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 
 // ----------------------------------------------------------------------------- stem
 // out[n,oy,ox,co] = swish( bias[co] + sum_{ky,kx,ci} w[ky,kx,ci,co] * norm(in[n,2oy+ky,2ox+kx,ci]) )
@@ -162,6 +170,81 @@ __global__ void __launch_bounds__(256) stem_kernel(const void* __restrict__ in_,
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = swish_f(acc[i]);
     st8(out + (gid >> 2) * 32 + cg * 8, acc);
+}
+
+// ----------------------------------------------------------------------------- stem, tiled
+// One CTA = two output rows of one crop (224 threads, one output pixel x 32 channels each).
+// The 5 input rows are loaded with 16-byte vectors, normalised through the LUT once and staged as fp32 in
+// shared memory (one extra zero pixel/row: TF-SAME puts its single pad row/column AFTER index 223).
+// The 27x32 BN-folded weights + 32 shifts arrive as a __grid_constant__ kernel parameter, so every FFMA
+// takes its weight straight from the constant bank (864 FFMA per thread, no weight loads at all).
+struct StemParams { float w[27 * 32]; float b[32]; };
+
+template <typename T, bool IN_U8, bool FAST>
+__global__ void __launch_bounds__(224) stem_tile_kernel(const void* __restrict__ in_, T* __restrict__ out,
+                                                        const __grid_constant__ StemParams sp,
+                                                        const float* __restrict__ lut) {
+    constexpr int ROWF = 225 * 3 + 1;              // floats per staged row (225 pixels incl. the zero pad pixel)
+    __shared__ float s_in[5 * ROWF];
+    __shared__ float s_lut[768];
+    const int tid = threadIdx.x;
+    const int n = blockIdx.y, oy0 = blockIdx.x * 2;
+    if (IN_U8) {
+        for (int i = tid; i < 768; i += 224) s_lut[i] = lut[i];
+        __syncthreads();
+    }
+    // stage rows 2*oy0 .. 2*oy0+4 (row 224 does not exist -> zeros)
+    if (IN_U8) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(in_) + (long long)n * 224 * 224 * 3;
+        for (int v = tid; v < 5 * 42; v += 224) {           // 42 x 16 bytes per input row
+            const int r = v / 42, q = v - r * 42;
+            const int iy = 2 * oy0 + r;
+            float* dst = &s_in[r * ROWF + q * 16];
+            if (iy < 224) {
+                const uint4 raw = *reinterpret_cast<const uint4*>(src + (long long)iy * 672 + q * 16);
+                const uint8_t* b = reinterpret_cast<const uint8_t*>(&raw);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dst[j] = s_lut[((q * 16 + j) % 3) * 256 + b[j]];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dst[j] = 0.f;
+            }
+        }
+    } else {
+        const float* src = reinterpret_cast<const float*>(in_) + (long long)n * 224 * 224 * 3;
+        for (int v = tid; v < 5 * 168; v += 224) {          // 168 x float4 per input row
+            const int r = v / 168, q = v - r * 168;
+            const int iy = 2 * oy0 + r;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (iy < 224) x = *reinterpret_cast<const float4*>(src + (long long)iy * 672 + q * 4);
+            float* dst = &s_in[r * ROWF + q * 4];
+            dst[0] = x.x; dst[1] = x.y; dst[2] = x.z; dst[3] = x.w;
+        }
+    }
+    if (tid < 15) s_in[(tid / 3) * ROWF + 672 + tid % 3] = 0.f;   // pad pixel (column 224) of the 5 rows
+    __syncthreads();
+    const int oyl = tid / 112, ox = tid - oyl * 112;
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = sp.b[c];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const float* row = &s_in[(2 * oyl + ky) * ROWF + 6 * ox];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {                       // kx*3 + ci
+            const float x = row[t];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[c] = fmaf(x, sp.w[(ky * 9 + t) * 32 + c], acc[c]);
+        }
+    }
+    T* dst = out + (((long long)n * 112 + oy0 + oyl) * 112 + ox) * 32;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = FAST ? swish_fast(acc[g * 8 + j]) : swish_f(acc[g * 8 + j]);
+        st8<T>(dst + g * 8, o);
+    }
 }
 
 // ----------------------------------------------------------------------------- 1x1 conv (CUDA-core GEMM)
@@ -313,13 +396,6 @@ __global__ void __launch_bounds__(256) dw_conv_kernel(const T* __restrict__ in, 
 // one row for its 8 channels: the (R-1)*S+KS input columns of each kernel row are loaded once and feed
 // all the taps that touch them (KS*KS loads per output -> ((R-1)*S+KS)*KS/R), the KS weights of the
 // current kernel row live in registers.  FAST selects the 1-MUFU swish (tanh.approx) of the 16-bit modes.
-__device__ __forceinline__ float swish_fast(float x) {
-    // x*sigmoid(x) = h + h*tanh(h), h = x/2  (MUFU.TANH: one SFU op instead of EX2 + RCP)
-    const float h = 0.5f * x;
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-    return fmaf(h, t, h);
-}
 
 template <typename T, int KS, int S, int R, bool FAST>
 __global__ void __launch_bounds__(256) dw_strip_kernel(const T* __restrict__ in, const float* __restrict__ w,  // [KS*KS][C]

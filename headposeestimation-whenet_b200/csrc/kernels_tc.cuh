@@ -283,7 +283,8 @@ int launch_pw_tc(cudaStream_t stream, const T* A, const void* Wt16, const float*
                  T* out, long long M, int K, int N, int hw, bool swish) {
     if (sizeof(T) != 2) return 1;
     if ((K & 7) || (N & 7) || M > 0x7fffffffLL) return 1;
-    // columns per CTA: whole N when it fits 256 TMEM columns, otherwise an even split into <=256 wide tiles
+    // columns per CTA: whole N when it fits 256 TMEM columns, otherwise an even split into <=256 wide tiles;
+    // then split further (A is re-read from L2, cheap) until the grid covers the 148 SMs about twice
     int n_tile = N;
     if (N > 256) {
         int parts = (N + 255) / 256;
@@ -291,6 +292,15 @@ int launch_pw_tc(cudaStream_t stream, const T* A, const void* Wt16, const float*
             n_tile = ((N + parts - 1) / parts + 15) & ~15;
             if (n_tile <= 256) break;
             ++parts;
+        }
+    }
+    {
+        const long long m_tiles = (M + BM - 1) / BM;
+        while (n_tile > 48 && m_tiles * ((N + n_tile - 1) / n_tile) < 296) {
+            const int parts = (N + n_tile - 1) / n_tile + 1;
+            const int nt = ((N + parts - 1) / parts + 15) & ~15;
+            if (nt >= n_tile) break;
+            n_tile = nt;
         }
     }
     const int umma_n = (n_tile + 15) & ~15;

@@ -97,6 +97,8 @@ struct whenet_ctx {
     int use_tc = 0;         // tensor-core kernels for the 1x1 convs
     bool tc_used = false;   // a tcgen05 kernel ran since the last timeout-flag check
     int dw_variant = 1;     // 0 = one output per thread, 1 = register-blocked strips
+    int stem_variant = 1;   // 0 = 4 threads / pixel straight from global, 1 = smem-tiled, weights in the constant bank
+    whenet::StemParams stem_params{};
     int use_fused = 0;      // K1: expand + depthwise in one kernel (16-bit storage only)
     int fused_max_block = 6;   // blocks 2..fused_max_block use K1
     std::vector<K1Plan> k1;
@@ -307,10 +309,14 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
     T* E = (T*)c->bufE;
     T* D = (T*)c->bufD;
     {
-        const long long total = (long long)nb * 112 * 112 * 4;
         Scope sc(c, "stem", (double)nb * (kImgElems * (IN_U8 ? 1.0 : 4.0) + 112.0 * 112 * 32 * sizeof(T)),
                  2.0 * nb * 112.0 * 112 * 27 * 32);
-        whenet::stem_kernel<T, IN_U8><<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_in, cur, c->w_stem, c->b_stem, c->lut, nb);
+        if (c->stem_variant == 0) {
+            const long long total = (long long)nb * 112 * 112 * 4;
+            whenet::stem_kernel<T, IN_U8><<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_in, cur, c->w_stem, c->b_stem, c->lut, nb);
+        } else {
+            whenet::stem_tile_kernel<T, IN_U8, (sizeof(T) == 2)><<<dim3(56, nb), 224, 0, c->stream>>>(d_in, cur, c->stem_params, c->lut);
+        }
         CK(cudaGetLastError());
     }
     if (taps) { int rc = add_tap<T>(c, "stem", cur, (size_t)nb * 112 * 112 * 32); if (rc) return rc; }
@@ -594,6 +600,8 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
         for (int ch = 0; ch < 3; ++ch)
             for (int v = 0; v < 256; ++v) lut[ch * 256 + v] = (float)((((double)v / 255.0) - mean[ch]) / sd[ch]);
         o_wstem = put(w); o_bstem = put(b); o_lut = put(lut);
+        memcpy(c->stem_params.w, w.data(), sizeof(c->stem_params.w));
+        memcpy(c->stem_params.b, b.data(), sizeof(c->stem_params.b));
     }
     // ---- 16 MBConv blocks
     for (size_t i = 0; i < c->blocks.size(); ++i) {
@@ -845,6 +853,7 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!c || !key) return fail(WHENET_EINVAL, "bad arguments");
     if (!strcmp(key, "tensor_cores")) { c->use_tc = value && c->precision != WHENET_PRECISION_FP32; return 0; }
     if (!strcmp(key, "dw_variant")) { c->dw_variant = value; return 0; }
+    if (!strcmp(key, "stem_variant")) { c->stem_variant = value; return 0; }
     if (!strcmp(key, "fused")) { c->use_fused = value && c->precision != WHENET_PRECISION_FP32; return 0; }
     if (!strcmp(key, "fused_max_block")) { c->fused_max_block = value; return 0; }
     if (!strcmp(key, "chunk")) {

@@ -10,9 +10,14 @@ crops = np.load(os.path.join(GOLD, "sample_crops.npy"))
 o = load_oracle(SNAP, np.float32); taps = {}
 ref = np.stack(o.get_angle(crops, taps), axis=1)
 for prec in os.environ.get("PRECS", "fp32,bf16,fp16").split(","):
-    for tc in ((0,) if prec == "fp32" else (0, 1)):
+    for tc in ((0,) if prec == "fp32" else tuple(int(t) for t in os.environ.get("TCS", "0,1").split(","))):
         m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=512)
         m.set_option("tensor_cores", tc)
+        for kv in filter(None, os.environ.get("OPTS", "").split(",")):
+            k, v = kv.split("=")
+            m.set_option(k, int(v))
+        if os.environ.get("CHUNK"):
+            m.set_option("chunk", int(os.environ["CHUNK"]))
         m.enable_taps(True)
         got = np.stack(m.get_angle(crops), axis=1)
         m.enable_taps(False)
