@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (repeatable)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -172,8 +173,10 @@ def main():
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
 
     net = whenet_b200.WHENet(whenet_b200.weights.DEFAULT_NPZ, device=local, precision=args.precision, max_batch=B)
-    if args.chunk:
-        net.set_option("chunk", args.chunk)
+    net.set_option("chunk", args.chunk if args.chunk else B)      # one pass per step: every layer sees the whole batch
+    for kv in args.opt:
+        k, v = kv.split("=")
+        net.set_option(k, int(v))
     stream = torch.cuda.Stream()          # a real (non-default) stream shared by the library, NCCL and the timing events
     torch.cuda.set_stream(stream)
     net.set_stream(stream.cuda_stream)
@@ -255,6 +258,7 @@ def main():
         for s in stats:
             nm = s["name"]
             f = "pw_conv(1x1)" if (nm.endswith(".expand") or nm.endswith(".project") or nm == "head.conv") else \
+                "k1_expand_dw(fused)" if nm.endswith(".k1") else \
                 "dw_conv" if nm.endswith(".dw") else "se_gate" if nm.endswith(".se") else nm
             a = fam.setdefault(f, {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "launches": 0})
             for k in ("ms", "bytes", "flops", "launches"):

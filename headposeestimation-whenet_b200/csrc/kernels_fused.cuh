@@ -1,22 +1,25 @@
 // kernels_fused.cuh - K1: the fused front half of an MBConv block.
 //
-//   expand 1x1 (tcgen05, accumulators in TMEM) -> BN shift + swish -> shared memory (never HBM)
+//   expand 1x1 (tcgen05, accumulators in TMEM, BN shift folded in as two extra K columns)
+//   -> swish -> shared memory (never HBM)
 //   -> depthwise KSxKS stride S, TF-SAME (CUDA-core FMA on the smem tile) -> BN shift + swish
 //   -> D (global, 16-bit) + deterministic SE squeeze partial sums
 //
 // One CTA owns a TH x TW tile of the depthwise OUTPUT of one crop.  The matching input halo tile
-// (IH x IW = (TH-1)*S+KS square, raster order = GEMM rows) is staged once in the UMMA K-major
-// SWIZZLE_128B layout; the expanded channels are then produced and consumed CC at a time:
+// (IH x IW = (TH-1)*S+KS square, raster order = GEMM rows) is staged once with cp.async in the UMMA
+// K-major SWIZZLE_128B layout; the expanded channels are then produced and consumed CC at a time:
 //
-//   for each chunk of CC expanded channels:
-//       W chunk -> smem ; tcgen05.mma  D[mt][128 x CC] = A[mt] (128 x Cin) * Wc^T   for every 128-row tile mt
-//       TMEM -> registers -> +shift, swish, ZERO for halo pixels outside the image (the depthwise pads the
-//               EXPANDED tensor with zeros, not the block input) -> 16-bit -> E[pixel][CC] in smem
-//       depthwise strips straight out of E (LDS.128), weights of one kernel row in registers
+//   for each chunk of CC expanded channels (W chunk + depthwise constants of chunk i+1 prefetched with cp.async):
+//       tcgen05.mma  D[mt][128 x CC] = [A | 1 1] (128 x (Cin+8)) * [Wc | shift_hi shift_lo]^T   for every 128-row tile mt
+//       TMEM -> registers -> swish, ZERO for halo pixels outside the image (the depthwise pads the EXPANDED
+//               tensor with zeros, not the block input) -> 16-bit -> E[pixel][CC] in smem
+//       depthwise strips straight out of E (ld.shared.v2), the KS weights of one kernel row from smem
 //       -> store D, accumulate the squeeze sums
 //
 // The expanded tensor (the largest activation of the network: 112*112*96 values per crop in block 2)
-// therefore never leaves the SM.
+// never leaves the SM.  The BN shift of the expand conv rides on the tensor core: A gets two constant
+// 1.0 columns, W gets the shift split into a bf16 high and low part (error 2^-17 relative), so the
+// epilogue has no bias loads or adds.
 #pragma once
 #include "kernels_tc.cuh"
 
@@ -28,9 +31,8 @@ using tc::BM;
 
 struct K1Params {
     const void* in;        // T [N][Hin][Hin][Cin]
-    const void* wt;        // T [Cexp][Cin]   (BN-folded, K-major)
-    const float* b_exp;    // [Cexp]
-    const float* w_dw;     // [KS*KS][Cexp]   (BN-folded)
+    const void* wt_aug;    // T [Cexp][Cin+8]   BN-folded weights, K-major, columns Cin / Cin+1 = shift hi / lo, rest 0
+    const float* w_dw;     // [KS*KS][Cexp]     (BN-folded)
     const float* b_dw;     // [Cexp]
     void* out;             // T [N][Ho][Ho][Cexp]
     float* partial;        // [N][tiles][Cexp]
@@ -38,64 +40,86 @@ struct K1Params {
     int TH, TW, IH, IW;    // output tile, input halo tile
     int tiles_x, tiles_y;
     int CC, n_chunks;      // expanded channels per chunk (multiple of 16), number of chunks
-    int mtiles;            // ceil(IH*IW / 128)
-    int nkb;               // ceil(Cin / 64)
+    int mtiles;            // ceil(IH*IW / 128)  (<= 3)
+    int cpr;               // 16-byte chunks per operand row incl. the ones/shift chunk, rounded up to even
+    int nkb;               // ceil(cpr / 8)
     int tmem_cols;         // power of two >= mtiles*CC
     int pitchE;            // bytes per E row = CC*2 + 16
     int PY;                // strip lanes in the depthwise phase = 256 / (CC/4)
+    int spr_log2;          // log2(strips per output row)
     uint32_t idesc;
-    int smem_A, smem_W, smem_E;   // byte sizes of the three regions (A and W multiples of 1024)
+    int smem_A, smem_W, smem_C, smem_E;   // region sizes in bytes (W and C are per buffer; both double-buffered)
 };
 
-template <typename T> __device__ __forceinline__ void unpack8(const uint4& raw, float (&v)[8]);
-template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& raw, float (&v)[8]) {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const uint32_t sz = valid ? 16u : 0u;     // src-size 0 -> 16 zero bytes
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
-template <> __device__ __forceinline__ void unpack8<__half>(const uint4& raw, float (&v)[8]) {
-    const __half2* h = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-template <typename T> __device__ __forceinline__ uint4 pack8(const float (&v)[8]);
-template <> __device__ __forceinline__ uint4 pack8<__nv_bfloat16>(const float (&v)[8]) {
-    uint4 t; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    return t;
+__device__ __forceinline__ void lds64(uint32_t addr, uint32_t& a, uint32_t& b) {
+    asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr));
 }
-template <> __device__ __forceinline__ uint4 pack8<__half>(const float (&v)[8]) {
-    uint4 t; __half2* h = reinterpret_cast<__half2*>(&t);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-    return t;
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+template <typename T> __device__ __forceinline__ void unpack2(uint32_t u, float& lo, float& hi);
+template <> __device__ __forceinline__ void unpack2<__nv_bfloat16>(uint32_t u, float& lo, float& hi) {
+    lo = __uint_as_float(u << 16);
+    hi = __uint_as_float(u & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void unpack2<__half>(uint32_t u, float& lo, float& hi) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+    lo = f.x; hi = f.y;
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <typename T> __device__ __forceinline__ uint32_t ones2();
+template <> __device__ __forceinline__ uint32_t ones2<__nv_bfloat16>() { return 0x3f803f80u; }
+template <> __device__ __forceinline__ uint32_t ones2<__half>() { return 0x3c003c00u; }
+
+// swizzled byte offset of 16-byte chunk c (0..7) of row r inside one K block ([rows][128 B], 8-row atoms of 1024 B)
+__device__ __forceinline__ uint32_t sw128(int r, int c) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
 template <typename T, int KS, int S, int R>
-__global__ void __launch_bounds__(256) k1_expand_dw_kernel(const K1Params p) {
+__global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_abort;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;                       // [nkb][mtiles*128 rows][128 B]   swizzled
-    uint8_t* sW = sA + p.smem_A;              // [nkb][CC rows][128 B]           swizzled
-    uint8_t* sE = sW + p.smem_W;              // [IH*IW rows (+slack)][pitchE]
-    float* s_red = reinterpret_cast<float*>(sE + p.smem_E);   // [PY][CC]
+    const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = smem0;                                  // [nkb][mtiles*128 rows][128 B]   swizzled
+    const uint32_t sW = sA + p.smem_A;                          // 2 x [nkb][CC rows][128 B]       swizzled
+    const uint32_t sC = sW + 2 * p.smem_W;                      // 2 x { b_dw[CC], w_dw[KS*KS][CC] } fp32
+    const uint32_t sE = sC + 2 * p.smem_C;                      // [IH*IW rows (+slack)][pitchE]
+    const uint32_t sR = sE + p.smem_E;                          // [PY][CC] fp32 squeeze partials
 
     const T* in = reinterpret_cast<const T*>(p.in);
-    const T* wt = reinterpret_cast<const T*>(p.wt);
+    const T* wt = reinterpret_cast<const T*>(p.wt_aug);
     T* out = reinterpret_cast<T*>(p.out);
 
     const int n = blockIdx.y, tile = blockIdx.x;
-    const int ty0 = (tile / p.tiles_x) * p.TH, tx0 = (tile % p.tiles_x) * p.TW;     // output-tile origin
-    const int iy0 = ty0 * S - p.pad, ix0 = tx0 * S - p.pad;                         // input-tile origin (may be < 0)
+    const int tyi = tile / p.tiles_x;
+    const int ty0 = tyi * p.TH, tx0 = (tile - tyi * p.tiles_x) * p.TW;             // output-tile origin
+    const int iy0 = ty0 * S - p.pad, ix0 = tx0 * S - p.pad;                       // input-tile origin (may be < 0)
     const int npix = p.IH * p.IW;
     const int rows_total = p.mtiles * BM;
-    const int kchunks = p.Cin >> 3;
+    const int kchunks = p.Cin >> 3;                     // data chunks per row; chunk `kchunks` holds the ones / the shift
+    const int Kaug = p.Cin + 8;
 
     if (tid == 0) {
         tc::mbar_init(&mbar, 1);
@@ -107,94 +131,134 @@ __global__ void __launch_bounds__(256) k1_expand_dw_kernel(const K1Params p) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
 
-    // ---- A: the input halo tile, rows in raster order, zero outside the image, zero pad chunk when Cin/8 is odd
+    // ---- A: the input halo tile (cp.async, zero-filled outside the image), + the ones chunk, + an even-count pad chunk
     {
         const T* in_n = in + (long long)n * p.Hin * p.Hin * p.Cin;
-        const int cpr = (kchunks + 1) & ~1;                  // chunks written per row
-        for (int idx = tid; idx < npix * cpr; idx += 256) {
-            const int r = idx / cpr, c = idx - r * cpr;
-            const int ty = r / p.IW, tx = r - ty * p.IW;
+        // one (pixel, chunk) item per step; walk pixels with a running (ty, tx) instead of dividing
+        const int items = npix * kchunks;
+        int r = tid / kchunks, c = tid - r * kchunks;
+        int ty = r / p.IW, tx = r - ty * p.IW;
+        const int dr = 256 / kchunks, dc = 256 - dr * kchunks;      // advance of (r, c) per step
+        const int dty = dr / p.IW, dtx = dr - dty * p.IW;
+        for (int idx = tid; idx < items; idx += 256) {
             const int iy = iy0 + ty, ix = ix0 + tx;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (c < kchunks && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Hin)
-                v = *reinterpret_cast<const uint4*>(in_n + ((long long)iy * p.Hin + ix) * p.Cin + c * 8);
-            const int kb = c >> 3, cc = c & 7;
-            *reinterpret_cast<uint4*>(sA + (size_t)kb * rows_total * 128 + (r >> 3) * 1024 + (r & 7) * 128 + ((cc ^ (r & 7)) << 4)) = v;
+            const bool valid = iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Hin;
+            const T* src = valid ? in_n + ((long long)iy * p.Hin + ix) * p.Cin + c * 8 : in_n;
+            cp_async16(sA + (uint32_t)(c >> 3) * rows_total * 128 + sw128(r, c & 7), src, valid);
+            c += dc; r += dr; ty += dty; tx += dtx;
+            if (c >= kchunks) { c -= kchunks; ++r; ++tx; }
+            if (tx >= p.IW) { tx -= p.IW; ++ty; }
+            if (tx >= p.IW) { tx -= p.IW; ++ty; }
+        }
+        const uint4 ones = make_uint4(ones2<T>(), 0u, 0u, 0u), zero = make_uint4(0u, 0u, 0u, 0u);
+        for (int rr = tid; rr < npix; rr += 256) {
+            sts128(sA + (uint32_t)(kchunks >> 3) * rows_total * 128 + sw128(rr, kchunks & 7), ones);
+            if (p.cpr > kchunks + 1)
+                sts128(sA + (uint32_t)((kchunks + 1) >> 3) * rows_total * 128 + sw128(rr, (kchunks + 1) & 7), zero);
         }
     }
+    // ---- prefetch of a W chunk + the depthwise constants of a chunk into buffer `buf`
+    auto prefetch_chunk = [&](int ch, int buf) {
+        const int cbase = ch * p.CC;
+        const uint32_t w_dst = sW + buf * p.smem_W;
+        const int per_row = p.cpr;                                 // data chunks + shift chunk (+ zero pad chunk)
+        for (int idx = tid; idx < p.CC * per_row; idx += 256) {
+            const int r = idx / per_row, c = idx - r * per_row;
+            const bool valid = c <= kchunks;
+            cp_async16(w_dst + (uint32_t)(c >> 3) * p.CC * 128 + sw128(r, c & 7),
+                       valid ? wt + (long long)(cbase + r) * Kaug + c * 8 : wt, valid);
+        }
+        const uint32_t c_dst = sC + buf * p.smem_C;
+        const int q = p.CC >> 2;                                   // 16-byte pieces per constant row
+        for (int idx = tid; idx < (KS * KS + 1) * q; idx += 256) {
+            const int row = idx / q, j = idx - row * q;
+            const float* src = row == 0 ? p.b_dw + cbase + j * 4 : p.w_dw + (long long)(row - 1) * p.Cexp + cbase + j * 4;
+            cp_async16(c_dst + (uint32_t)(row * p.CC + j * 4) * 4, src, true);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch_chunk(0, 0);
+
+    // ---- per-thread constants of the two compute phases
+    // epilogue 1: warp w reads TMEM lane quadrant (w & 3); warps 0-3 take the low 16-column units, 4-7 the high ones
+    const int q4 = warp & 3;
+    uint32_t e_row[3];
+    bool e_inside[3], e_valid[3];
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt) {
+        const int r = mt * BM + q4 * 32 + lane;
+        const int ty = r / p.IW, tx = r - ty * p.IW;
+        const int iy = iy0 + ty, ix = ix0 + tx;
+        e_valid[mt] = mt < p.mtiles && r < npix;
+        e_inside[mt] = e_valid[mt] && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Hin;
+        e_row[mt] = sE + (uint32_t)r * p.pitchE;
+    }
+    const int units = p.CC >> 4;
+    const int u0 = (warp >> 2) ? (units + 1) / 2 : 0;
+    const int u1 = (warp >> 2) ? units : (units + 1) / 2;
+    // depthwise: thread = (4-channel vector cv, strip lane py)
+    const int CVc = p.CC >> 2;
+    const int py = tid / CVc, cv = tid - py * CVc;
+    const bool dw_active = py < p.PY;
+    const int nstrips = p.TH << p.spr_log2;
+    const uint32_t e_rowstride = (uint32_t)p.IW * p.pitchE;
+    constexpr int NCOL = (R - 1) * S + KS;
+    T* const out_n = out + (long long)n * p.Ho * p.Ho * p.Cexp;
+
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = s_tmem_base;
 
-    // depthwise-phase thread coordinates
-    const int CVc = p.CC >> 2;                             // 4-channel vectors per chunk
-    const int cv = tid % CVc, py = tid / CVc;
-    const bool dw_active = py < p.PY;
-    const int spr = (p.TW + R - 1) / R;
-    const int nstrips = p.TH * spr;
-    constexpr int NCOL = (R - 1) * S + KS;
-
     for (int ch = 0; ch < p.n_chunks; ++ch) {
-        const int cbase = ch * p.CC;                        // first expanded channel of this chunk
-        // ---- W chunk: CC rows (output channels) x Cin, swizzled K-major
-        {
-            const int cpr = (kchunks + 1) & ~1;
-            for (int idx = tid; idx < p.CC * cpr; idx += 256) {
-                const int r = idx / cpr, c = idx - r * cpr;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (c < kchunks && cbase + r < p.Cexp)
-                    v = *reinterpret_cast<const uint4*>(wt + (long long)(cbase + r) * p.Cin + c * 8);
-                const int kb = c >> 3, cc = c & 7;
-                *reinterpret_cast<uint4*>(sW + (size_t)kb * p.CC * 128 + (r >> 3) * 1024 + (r & 7) * 128 + ((cc ^ (r & 7)) << 4)) = v;
-            }
-        }
+        const int buf = ch & 1;
+        const int cbase = ch * p.CC;
+        // operands of this chunk (and, the first time, A) have landed; make them visible to the tensor core
+        asm volatile("cp.async.wait_all;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int ksteps_total = p.cpr >> 1;
             for (int mt = 0; mt < p.mtiles; ++mt) {
-                for (int kb = 0; kb < p.nkb; ++kb) {
-                    const int krem = min(BK, p.Cin - kb * BK);
-                    const int ksteps = (krem + 15) >> 4;
-                    const uint64_t ad = tc::make_desc(tc::smem_u32(sA + (size_t)kb * rows_total * 128 + (size_t)mt * BM * 128));
-                    const uint64_t bd = tc::make_desc(tc::smem_u32(sW + (size_t)kb * p.CC * 128));
-                    for (int k = 0; k < ksteps; ++k)
-                        tc::umma_f16(tmem_d + (uint32_t)(mt * p.CC), ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), p.idesc, (kb | k) ? 1u : 0u);
+                for (int ks = 0; ks < ksteps_total; ++ks) {
+                    const int kb = ks >> 2, k = ks & 3;
+                    const uint64_t ad = tc::make_desc(sA + (uint32_t)kb * rows_total * 128 + (uint32_t)mt * BM * 128);
+                    const uint64_t bd = tc::make_desc(sW + buf * p.smem_W + (uint32_t)kb * p.CC * 128);
+                    tc::umma_f16(tmem_d + (uint32_t)(mt * p.CC), ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), p.idesc, ks ? 1u : 0u);
                 }
             }
             tc::umma_commit(&mbar);
         }
+        // next chunk's W + constants stream in behind the MMAs / epilogue / depthwise of this one
+        if (ch + 1 < p.n_chunks) prefetch_chunk(ch + 1, buf ^ 1);
         if (!tc::mbar_wait(&mbar, ch & 1)) s_abort = 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         __syncthreads();
         const bool ok = !s_abort;
 
-        // ---- epilogue 1: TMEM -> E.  warp w reads lane quadrant (w & 3); warps 0-3 take the low column units, 4-7 the high
+        // ---- epilogue 1: TMEM -> swish -> E (16-bit).  The BN shift is already in the accumulator.
         if (ok) {
-            const int q = warp & 3;
-            const int units = p.CC >> 4;                    // 16-column units in the chunk
-            const int u0 = (warp >> 2) ? (units + 1) / 2 : 0;
-            const int u1 = (warp >> 2) ? units : (units + 1) / 2;
-            for (int mt = 0; mt < p.mtiles; ++mt) {
-                const int r = mt * BM + q * 32 + lane;
-                const int ty = r / p.IW, tx = r - ty * p.IW;
-                const int iy = iy0 + ty, ix = ix0 + tx;
-                const bool inside = r < npix && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Hin;
-                for (int u = u0; u < u1; ++u) {
-                    float v[16];
-                    tc::tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.CC + u * 16), v);
-                    if (r < npix) {
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            float o[8];
-                            const float* bp = p.b_exp + cbase + u * 16 + h * 8;
-                            const float4 b0 = *reinterpret_cast<const float4*>(bp), b1 = *reinterpret_cast<const float4*>(bp + 4);
-                            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            for (int mt = 0; mt < 3; ++mt) {
+                if (mt < p.mtiles) {
+                    for (int u = u0; u < u1; ++u) {
+                        float v[16];
+                        tc::tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mt * p.CC + u * 16), v);
+                        if (e_valid[mt]) {
+                            uint4 lo, hi;
+                            if (e_inside[mt]) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] = inside ? swish_fast(v[h * 8 + j] + bb[j]) : 0.f;
-                            *reinterpret_cast<uint4*>(sE + (size_t)r * p.pitchE + (u * 16 + h * 8) * 2) = pack8<T>(o);
+                                for (int j = 0; j < 16; ++j) v[j] = swish_fast(v[j]);
+                                lo = make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
+                                hi = make_uint4(pack2<T>(v[8], v[9]), pack2<T>(v[10], v[11]), pack2<T>(v[12], v[13]), pack2<T>(v[14], v[15]));
+                            } else {
+                                lo = make_uint4(0u, 0u, 0u, 0u);
+                                hi = lo;
+                            }
+                            sts128(e_row[mt] + u * 32, lo);
+                            sts128(e_row[mt] + u * 32 + 16, hi);
                         }
                     }
                 }
@@ -203,71 +267,73 @@ __global__ void __launch_bounds__(256) k1_expand_dw_kernel(const K1Params p) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
 
-        // ---- depthwise on E: thread = (4-channel vector, strip lane); 8-byte LDS, fp32 FMA
+        // ---- depthwise on E: 8-byte ld.shared, fp32 FMA, weights of one kernel row from smem
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
         if (ok && dw_active) {
             const int c0 = cbase + cv * 4;
-            const float4 bq = *reinterpret_cast<const float4*>(p.b_dw + c0);
-            const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
-            T* out_n = out + (long long)n * p.Ho * p.Ho * p.Cexp;
-            const uint8_t* e_cv = sE + cv * 8;
+            const uint32_t cst = sC + buf * p.smem_C + (uint32_t)cv * 16;         // this thread's column of the constants
+            const float4 bq = lds_f4(cst);
+            const uint32_t e_cv = sE + (uint32_t)cv * 8;
             for (int sidx = py; sidx < nstrips; sidx += p.PY) {
-                const int oyl = sidx / spr, oxl0 = (sidx - oyl * spr) * R;
+                const int oyl = sidx >> p.spr_log2, oxl0 = (sidx - (oyl << p.spr_log2)) * R;
                 float acc[R][4];
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[r][i] = bb[i];
+                for (int r = 0; r < R; ++r) { acc[r][0] = bq.x; acc[r][1] = bq.y; acc[r][2] = bq.z; acc[r][3] = bq.w; }
+                uint32_t erow = e_cv + (uint32_t)(oyl * S) * e_rowstride + (uint32_t)(oxl0 * S) * p.pitchE;
 #pragma unroll
                 for (int ky = 0; ky < KS; ++ky) {
-                    float wr[KS][4];
+                    float4 wr[KS];
 #pragma unroll
-                    for (int kx = 0; kx < KS; ++kx) {
-                        const float4 w0 = *reinterpret_cast<const float4*>(p.w_dw + (ky * KS + kx) * p.Cexp + c0);
-                        wr[kx][0] = w0.x; wr[kx][1] = w0.y; wr[kx][2] = w0.z; wr[kx][3] = w0.w;
-                    }
-                    const uint8_t* erow = e_cv + (size_t)((oyl * S + ky) * p.IW + oxl0 * S) * p.pitchE;
+                    for (int kx = 0; kx < KS; ++kx) wr[kx] = lds_f4(cst + (uint32_t)((1 + ky * KS + kx) * p.CC) * 4);
+                    uint32_t ea = erow;
 #pragma unroll
                     for (int col = 0; col < NCOL; ++col) {
-                        float x[4];
-                        ld4(reinterpret_cast<const T*>(erow + (size_t)col * p.pitchE), x);
+                        uint32_t a, b;
+                        lds64(ea, a, b);
+                        ea += p.pitchE;
+                        float x0, x1, x2, x3;
+                        unpack2<T>(a, x0, x1);
+                        unpack2<T>(b, x2, x3);
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            const int kx = col - r * S;
+                            const int kx = col - r * S;          // compile-time after unrolling
                             if (kx >= 0 && kx < KS) {
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) acc[r][i] = fmaf(x[i], wr[kx][i], acc[r][i]);
+                                acc[r][0] = fmaf(x0, wr[kx].x, acc[r][0]);
+                                acc[r][1] = fmaf(x1, wr[kx].y, acc[r][1]);
+                                acc[r][2] = fmaf(x2, wr[kx].z, acc[r][2]);
+                                acc[r][3] = fmaf(x3, wr[kx].w, acc[r][3]);
                             }
                         }
                     }
+                    erow += e_rowstride;
                 }
                 const int oy = ty0 + oyl;
+                T* dst = out_n + ((long long)oy * p.Ho + tx0 + oxl0) * p.Cexp + c0;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const int oxl = oxl0 + r, ox = tx0 + oxl;
-                    if (oxl < p.TW && oy < p.Ho && ox < p.Ho) {
+                    if (oxl0 + r < p.TW && oy < p.Ho && tx0 + oxl0 + r < p.Ho) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[r][i] = swish_fast(acc[r][i]);
-                        st4(out_n + ((long long)oy * p.Ho + ox) * p.Cexp + c0, acc[r]);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) sum[i] += Store<T>::rnd(acc[r][i]);
+                        for (int i = 0; i < 4; ++i) { acc[r][i] = swish_fast(acc[r][i]); sum[i] += acc[r][i]; }
+                        uint2 o;
+                        o.x = pack2<T>(acc[r][0], acc[r][1]);
+                        o.y = pack2<T>(acc[r][2], acc[r][3]);
+                        *reinterpret_cast<uint2*>(dst + (long long)r * p.Cexp) = o;
                     }
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) s_red[py * p.CC + cv * 4 + i] = sum[i];
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sR + (uint32_t)(py * p.CC + cv * 4) * 4),
+                         "f"(sum[0]), "f"(sum[1]), "f"(sum[2]), "f"(sum[3]) : "memory");
         }
         __syncthreads();
         if (ok && dw_active && py == 0) {
-            float tot[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int y = 0; y < p.PY; ++y)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) tot[i] += s_red[y * p.CC + cv * 4 + i];
-            float* dst = p.partial + ((long long)n * gridDim.x + tile) * p.Cexp + cbase + cv * 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = tot[i];
+            float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int y = 0; y < p.PY; ++y) {
+                const float4 t = lds_f4(sR + (uint32_t)(y * p.CC + cv * 4) * 4);
+                tot.x += t.x; tot.y += t.y; tot.z += t.z; tot.w += t.w;
+            }
+            *reinterpret_cast<float4*>(p.partial + ((long long)n * gridDim.x + tile) * p.Cexp + cbase + cv * 4) = tot;
         }
-        // E, s_red and TMEM are free again after the barrier at the top of the next chunk (W fill + sync)
+        // E, the squeeze scratch and TMEM are reused only after the barrier at the top of the next chunk
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -275,38 +341,60 @@ __global__ void __launch_bounds__(256) k1_expand_dw_kernel(const K1Params p) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)p.tmem_cols) : "memory");
 }
 
-// Tile plan for one block; returns false when K1 does not cover the configuration.
-inline bool plan_k1(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, bool is_bf16, K1Params* p, int* R_out, size_t* smem_out) {
-    int TH, R;
-    if (Ho % 8 == 0 && s == 2 && k == 3) { TH = 8; R = 2; }          // 112->56: 17x17 halo, 3 GEMM tiles
-    else if (Ho % 14 == 0 && s == 1) { TH = 14; R = 7; }             // 56/28/14 maps, stride 1: 16x16 / 18x18 halo
-    else if (Ho % 7 == 0) { TH = 7; R = 7; }                         // stride-2 5x5 / 3x3 onto 28 / 14 / 7
-    else return false;
+// Tile plan for one block: try a few tile shapes x chunk widths, prefer plans that let two CTAs share an SM
+// (<= 110 KB shared memory, <= 256 TMEM columns), then the most work per CTA.  Returns false when K1 cannot run it.
+inline bool plan_k1_candidate(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, bool is_bf16, int TH, int TW, int R, int CC,
+                              K1Params* p, size_t* smem_out) {
+    if (Ho % TH || Ho % TW || Cexp % CC || TW % R) return false;
     p->Hin = Hin; p->Ho = Ho; p->Cin = Cin; p->Cexp = Cexp; p->pad = pad;
-    p->TH = TH; p->TW = TH;
-    p->IH = (TH - 1) * s + k; p->IW = p->IH;
-    p->tiles_x = Ho / TH; p->tiles_y = Ho / TH;
+    p->TH = TH; p->TW = TW;
+    p->IH = (TH - 1) * s + k; p->IW = (TW - 1) * s + k;
+    p->tiles_x = Ho / TW; p->tiles_y = Ho / TH;
     p->mtiles = (p->IH * p->IW + BM - 1) / BM;
-    p->nkb = (Cin + BK - 1) / BK;
-    // chunk: largest divisor of Cexp that is a multiple of 16, <= 128, with mtiles*CC <= 256 TMEM columns
-    int CC = 0;
-    for (int c = 16; c <= 128; c += 16)
-        if (Cexp % c == 0 && p->mtiles * c <= 256) CC = c;
-    if (!CC) return false;
+    if (p->mtiles > 3 || p->mtiles * CC > 512) return false;
+    p->cpr = ((Cin >> 3) + 1 + 1) & ~1;
+    p->nkb = (p->cpr + 7) / 8;
     p->CC = CC; p->n_chunks = Cexp / CC;
     int cols = 32;
     while (cols < p->mtiles * CC) cols <<= 1;
     p->tmem_cols = cols;
     p->pitchE = CC * 2 + 16;
     p->PY = 256 / (CC / 4);
+    if (p->PY < 1) return false;
+    const int spr = TW / R;
+    p->spr_log2 = spr == 1 ? 0 : spr == 2 ? 1 : spr == 4 ? 2 : -1;
+    if (p->spr_log2 < 0) return false;
     p->idesc = tc::make_idesc(is_bf16, CC);
     p->smem_A = p->nkb * p->mtiles * BM * 128;
     p->smem_W = ((p->nkb * CC * 128) + 1023) & ~1023;
-    // slack rows: a strip whose tail lies beyond TW still LOADS (its results are discarded)
-    p->smem_E = ((p->IH * p->IW + 2 * p->IW + 16) * p->pitchE + 15) & ~15;
-    *R_out = R;
-    *smem_out = (size_t)p->smem_A + p->smem_W + p->smem_E + (size_t)p->PY * CC * 4 + 1024;
+    p->smem_C = (((k * k + 1) * CC * 4) + 1023) & ~1023;
+    p->smem_E = (((p->IH * p->IW + 16) * p->pitchE) + 1023) & ~1023;
+    *smem_out = (size_t)p->smem_A + 2 * p->smem_W + 2 * p->smem_C + p->smem_E + (size_t)p->PY * CC * 4 + 1024;
     return *smem_out <= 200 * 1024;
+}
+
+inline bool plan_k1(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, bool is_bf16, K1Params* p, int* R_out, size_t* smem_out) {
+    struct Cand { int th, tw, r; };
+    const Cand s1[] = {{14, 14, 7}, {7, 14, 7}, {7, 7, 7}};
+    const Cand s2k3[] = {{8, 8, 2}, {7, 7, 7}};
+    const Cand s2[] = {{7, 7, 7}};
+    const Cand* cands = s == 1 ? s1 : (k == 3 ? s2k3 : s2);
+    const int ncand = s == 1 ? 3 : (k == 3 ? 2 : 1);
+    bool found = false;
+    double best = -1;
+    for (int i = 0; i < ncand; ++i)
+        for (int cc = 128; cc >= 16; cc -= 16) {
+            K1Params q{};
+            size_t smem = 0;
+            if (!plan_k1_candidate(Hin, Ho, Cin, Cexp, k, s, pad, is_bf16, cands[i].th, cands[i].tw, cands[i].r, cc, &q, &smem)) continue;
+            const bool two = smem <= 110 * 1024 && q.tmem_cols <= 256;
+            // score: co-residency first, then depthwise work items per chunk (parallelism inside the CTA)
+            const double items = (double)(cands[i].th * (cands[i].tw / cands[i].r)) * (cc / 4);
+            // few chunks matter too: every chunk costs three CTA-wide barriers
+            const double score = (two ? 300 : 0) + (items > 512 ? 512 : items) - 6.0 * q.n_chunks;
+            if (score > best) { best = score; *p = q; *R_out = cands[i].r; *smem_out = smem; found = true; }
+        }
+    return found;
 }
 
 template <typename T>

@@ -83,6 +83,7 @@ struct BlockW {   // device pointers into the fp32 arena
     float *w_se2 = nullptr, *b_se2 = nullptr;     // [cse][cexp], [cexp]
     float *w_proj = nullptr, *b_proj = nullptr;   // [cexp][cout], [cout]
     void *wt_exp = nullptr, *wt_proj = nullptr;   // 16-bit [N][K] copies for the tensor-core path
+    void* wt_exp_aug = nullptr;                   // 16-bit [cexp][cin+8]: weights | shift_hi | shift_lo | 0... (K1)
 };
 
 struct K1Plan { bool valid = false; whenet::fused::K1Params p{}; int R = 0; size_t smem = 0; };
@@ -329,7 +330,7 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
         if constexpr (sizeof(T) == 2) {
             if (c->use_fused && c->k1[i].valid && b.idx <= c->fused_max_block) {
                 whenet::fused::K1Params p = c->k1[i].p;
-                p.in = cur; p.wt = w.wt_exp; p.b_exp = w.b_exp; p.w_dw = w.w_dw; p.b_dw = w.b_dw; p.out = D; p.partial = c->d_partial;
+                p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw; p.b_dw = w.b_dw; p.out = D; p.partial = c->d_partial;
                 snprintf(nm, sizeof nm, "b%02d.k1", b.idx);
                 Scope sc(c, nm, (double)nb * ((double)b.hin * b.hin * b.cin + (double)b.hout * b.hout * b.cexp) * sizeof(T),
                          2.0 * nb * ((double)b.hin * b.hin * b.cin * b.cexp + (double)b.hout * b.hout * b.k * b.k * b.cexp));
@@ -558,7 +559,9 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
                                                   while (arena.size() % 4) arena.push_back(0.f); return off; };
     auto put16 = [&](const std::vector<float>& v) { size_t off = arena16src.size(); arena16src.insert(arena16src.end(), v.begin(), v.end());
                                                     while (arena16src.size() % 8) arena16src.push_back(0.f); return off; };
-    struct Off { size_t w_exp, b_exp, w_dw, b_dw, w_se1t, b_se1, w_se2, b_se2, w_proj, b_proj, t_exp, t_proj; };
+    struct Off { size_t w_exp, b_exp, w_dw, b_dw, w_se1t, b_se1, w_se2, b_se2, w_proj, b_proj, t_exp, t_proj, t_aug; };
+    // values of the augmented expand weights; shift columns are filled after 16-bit rounding of the high part
+    std::vector<std::pair<size_t, float>> shift_lo_fix;   // (index in arena16src of the hi column, full-precision shift)
     std::vector<Off> offs(c->blocks.size());
     int conv = 0, dwc = 0, bn = 0;
     auto conv_name = [&]() { return "conv2d_" + std::to_string(++conv); };
@@ -609,6 +612,15 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
         Off& o = offs[i];
         if (b.has_expand) {
             if (!pack_pw(b.cin, b.cexp, &o.w_exp, &o.b_exp, &o.t_exp)) return fail(WHENET_ESHAPE, "%s", err.c_str());
+            // [cexp][cin+8] copy for K1: the BN shift rides in two extra K columns (hi + lo 16-bit parts)
+            const int ka = b.cin + 8;
+            std::vector<float> aug((size_t)b.cexp * ka, 0.f);
+            for (int n = 0; n < b.cexp; ++n) {
+                for (int k = 0; k < b.cin; ++k) aug[(size_t)n * ka + k] = arena16src[o.t_exp + (size_t)n * b.cin + k];
+                aug[(size_t)n * ka + b.cin] = arena[o.b_exp + n];
+            }
+            o.t_aug = put16(aug);
+            for (int n = 0; n < b.cexp; ++n) shift_lo_fix.push_back({o.t_aug + (size_t)n * ka + b.cin, arena[o.b_exp + n]});
         }
         {
             const std::string nm = "depthwise_conv2d_" + std::to_string(++dwc);
@@ -671,6 +683,14 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
             if (c->precision == WHENET_PRECISION_BF16) { __nv_bfloat16 v = to16<__nv_bfloat16>(arena16src[i]); memcpy(&h16[i], &v, 2); }
             else { __half v = to16<__half>(arena16src[i]); memcpy(&h16[i], &v, 2); }
         }
+        // lo part of every K1 shift: what the 16-bit rounding of the hi part lost
+        for (auto& fx : shift_lo_fix) {
+            float hi;
+            if (c->precision == WHENET_PRECISION_BF16) { __nv_bfloat16 v; memcpy(&v, &h16[fx.first], 2); hi = __bfloat162float(v);
+                                                         __nv_bfloat16 lo = __float2bfloat16_rn(fx.second - hi); memcpy(&h16[fx.first + 1], &lo, 2); }
+            else { __half v; memcpy(&v, &h16[fx.first], 2); hi = __half2float(v);
+                   __half lo = __float2half_rn(fx.second - hi); memcpy(&h16[fx.first + 1], &lo, 2); }
+        }
         CK(cudaMalloc(&c->d_arena16, h16.size() * 2 + 256));
         CK(cudaMemcpy(c->d_arena16, h16.data(), h16.size() * 2, cudaMemcpyHostToDevice));
         base16 = (char*)c->d_arena16;
@@ -683,6 +703,7 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
         if (c->blocks[i].has_expand) {
             w.w_exp = A + o.w_exp; w.b_exp = A + o.b_exp;
             w.wt_exp = base16 ? base16 + o.t_exp * 2 : nullptr;
+            w.wt_exp_aug = base16 ? base16 + o.t_aug * 2 : nullptr;
         }
         w.w_dw = A + o.w_dw; w.b_dw = A + o.b_dw;
         w.w_se1t = A + o.w_se1t; w.b_se1 = A + o.b_se1; w.w_se2 = A + o.w_se2; w.b_se2 = A + o.b_se2;
