@@ -376,7 +376,7 @@ inline bool plan_k1_candidate(int Hin, int Ho, int Cin, int Cexp, int k, int s, 
 inline bool plan_k1(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, bool is_bf16, K1Params* p, int* R_out, size_t* smem_out) {
     struct Cand { int th, tw, r; };
     const Cand s1[] = {{14, 14, 7}, {7, 14, 7}, {7, 7, 7}};
-    const Cand s2k3[] = {{8, 8, 2}, {7, 7, 7}};
+    const Cand s2k3[] = {{8, 8, 4}, {7, 7, 7}};
     const Cand s2[] = {{7, 7, 7}};
     const Cand* cands = s == 1 ? s1 : (k == 3 ? s2k3 : s2);
     const int ncand = s == 1 ? 3 : (k == 3 ? 2 : 1);
@@ -407,7 +407,7 @@ int launch_k1(cudaStream_t stream, const K1Params& p, int k, int s, int R, size_
         kfn<<<grid, 256, smem, stream>>>(p);                                                                     \
         return 0;                                                                                                \
     } while (0)
-    if (k == 3 && s == 2 && R == 2) K1(3, 2, 2);
+    if (k == 3 && s == 2 && R == 4) K1(3, 2, 4);
     if (k == 3 && s == 1 && R == 7) K1(3, 1, 7);
     if (k == 5 && s == 1 && R == 7) K1(5, 1, 7);
     if (k == 5 && s == 2 && R == 7) K1(5, 2, 7);

@@ -100,8 +100,8 @@ struct whenet_ctx {
     int dw_variant = 1;     // 0 = one output per thread, 1 = register-blocked strips
     int stem_variant = 1;   // 0 = 4 threads / pixel straight from global, 1 = smem-tiled, weights in the constant bank
     whenet::StemParams stem_params{};
-    int use_fused = 0;      // K1: expand + depthwise in one kernel (16-bit storage only)
-    int fused_max_block = 6;   // blocks 2..fused_max_block use K1
+    int use_fused = 0;      // K1: expand + depthwise in one kernel (16-bit storage only; default on for bf16/fp16)
+    int fused_max_block = 16;  // blocks 2..fused_max_block use K1
     std::vector<K1Plan> k1;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     bool weights_loaded = false;
@@ -532,7 +532,8 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
             pl.valid = whenet::fused::plan_k1(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, precision == WHENET_PRECISION_BF16,
                                               &pl.p, &pl.R, &pl.smem);
         }
-    if (const char* e3 = getenv("WHENET_FUSED")) c->use_fused = atoi(e3);
+    c->use_fused = precision != WHENET_PRECISION_FP32;
+    if (const char* e3 = getenv("WHENET_FUSED")) c->use_fused = atoi(e3) && precision != WHENET_PRECISION_FP32;
     CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
