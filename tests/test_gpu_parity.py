@@ -108,6 +108,7 @@ def test_bf16_taps_vs_oracle(tc, oracle32, sample_crops):
     import whenet_b200
     m = whenet_b200.WHENet(SNAP, device=0, precision="bf16", max_batch=8)
     m.set_option("tensor_cores", tc)
+    m.set_option("fused", 0)
     taps = {}
     oracle32.get_angle(sample_crops, taps)
     m.enable_taps(True)
@@ -170,6 +171,7 @@ def test_tensor_core_path_matches_simt(sample_crops, jitter_crops):
     for tc in (0, 1):
         m = whenet_b200.WHENet(SNAP, device=0, precision="bf16", max_batch=8)
         m.set_option("tensor_cores", tc)
+        m.set_option("fused", 0)
         out.append(np.stack(m.get_angle(crops), axis=1))
         m.close()
     assert np.abs(out[0] - out[1]).max() < 1.5
@@ -196,6 +198,7 @@ def test_dw_variants_agree(prec, sample_crops, jitter_crops):
         m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=8)
         m.set_option("dw_variant", v)
         m.set_option("tensor_cores", 0)
+        m.set_option("fused", 0)
         out.append(np.stack(m.get_angle(crops), axis=1))
         m.close()
     if prec == "fp32":
