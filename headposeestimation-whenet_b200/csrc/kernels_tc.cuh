@@ -329,6 +329,293 @@ int launch_pw_tc(cudaStream_t stream, const T* A, const void* Wt16, const float*
     return 0;
 }
 
+// ----------------------------------------------------------------------------- pw_tc2: cp.async ring
+// Same contract as pw_tc_kernel, different data movement:
+//   * operand K blocks travel global -> shared with cp.async (16 B, zero-fill for tails) through a ring of
+//     n_stages stages, several blocks in flight, no register staging;
+//   * the SE gate is applied IN shared memory by the thread that copied the chunk (so no extra barrier):
+//       GATE == 1: on the A rows (tiles may span up to four crops; their gate rows sit in smem)
+//       GATE == 2: on the W rows (per-crop tiling: a tile never leaves its crop, used while H*W >= 784)
+//   * stage reuse is gated by the mbarrier of the previous block's tcgen05.commit.
+__device__ __forceinline__ void cp_async16_z(uint32_t dst, const void* src, bool valid) {
+    const uint32_t sz = valid ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128_(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+template <typename T> __device__ __forceinline__ uint4 scale8s(uint4 raw, uint32_t gaddr);   // gate values from smem
+template <> __device__ __forceinline__ uint4 scale8s<__nv_bfloat16>(uint4 raw, uint32_t gaddr) {
+    float4 g0, g1;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g0.x), "=f"(g0.y), "=f"(g0.z), "=f"(g0.w) : "r"(gaddr));
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g1.x), "=f"(g1.y), "=f"(g1.z), "=f"(g1.w) : "r"(gaddr + 16));
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h[i]);
+        h[i] = __floats2bfloat162_rn(f.x * gg[2 * i], f.y * gg[2 * i + 1]);
+    }
+    return raw;
+}
+template <> __device__ __forceinline__ uint4 scale8s<__half>(uint4 raw, uint32_t gaddr) {
+    float4 g0, g1;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g0.x), "=f"(g0.y), "=f"(g0.z), "=f"(g0.w) : "r"(gaddr));
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g1.x), "=f"(g1.y), "=f"(g1.z), "=f"(g1.w) : "r"(gaddr + 16));
+    __half2* h = reinterpret_cast<__half2*>(&raw);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __half22float2(h[i]);
+        h[i] = __floats2half2_rn(f.x * gg[2 * i], f.y * gg[2 * i + 1]);
+    }
+    return raw;
+}
+
+template <typename T, bool SWISH, int GATE, bool RESID>
+__global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, const T* __restrict__ Wt,
+                                                     const float* __restrict__ bias, const float* __restrict__ gate,
+                                                     const T* __restrict__ resid, T* __restrict__ out,
+                                                     int M, int K, int N, int hw,
+                                                     int n_tile, int umma_n, int tmem_cols, int n_stages,
+                                                     int tiles_per_crop,     // GATE == 2 only
+                                                     uint32_t idesc) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t mbar[4];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ int s_abort;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int w_stage_bytes = umma_n * BK * 2;
+    const uint32_t stage_bytes = A_STAGE_BYTES + w_stage_bytes;
+    const uint32_t sG = smem0 + n_stages * stage_bytes;          // gate rows: [<=4 crops][K] fp32 (GATE only)
+
+    // ---- tile -> rows
+    int m0, rows_valid, crop0;
+    if (GATE == 2) {
+        const int crop = blockIdx.y / tiles_per_crop, t = blockIdx.y - crop * tiles_per_crop;
+        m0 = crop * hw + t * BM;
+        rows_valid = min(BM, hw - t * BM);
+        crop0 = crop;
+    } else {
+        m0 = blockIdx.y * BM;
+        rows_valid = min(BM, M - m0);
+        crop0 = GATE ? m0 / hw : 0;
+    }
+    const int n0 = blockIdx.x * n_tile;
+    const int n_valid = min(n_tile, N - n0);
+    const int nkb = (K + BK - 1) / BK;
+    const int kchunks = K >> 3;
+
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(&mbar[i], 1);
+        s_abort = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"((uint32_t)tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // gate rows of the crops this tile touches -> smem (joins the first cp.async group)
+    if (GATE) {
+        const int ncrops = GATE == 2 ? 1 : ((m0 + rows_valid - 1) / hw - crop0 + 1);
+        const int q = K >> 2;
+        for (int idx = tid; idx < ncrops * q; idx += 128) {
+            const int cr = idx / q, j = idx - cr * q;
+            cp_async16_z(sG + (uint32_t)(cr * K + j * 4) * 4, gate + (long long)(crop0 + cr) * K + j * 4, true);
+        }
+    }
+    auto fill = [&](int kb) {
+        const int s = kb % n_stages;
+        const uint32_t a_st = smem0 + s * stage_bytes, w_st = a_st + A_STAGE_BYTES;
+        const int kc0 = kb * 8;
+        const int cb = min(8, kchunks - kc0), cbp = (cb + 1) & ~1;
+        for (int idx = tid; idx < BM * cbp; idx += 128) {
+            const int r = idx / cbp, c = idx - r * cbp;
+            const bool valid = r < rows_valid && c < cb;
+            cp_async16_z(a_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4),
+                         valid ? A + (long long)(m0 + r) * K + (kc0 + c) * 8 : A, valid);
+        }
+        for (int idx = tid; idx < umma_n * cbp; idx += 128) {
+            const int r = idx / cbp, c = idx - r * cbp;
+            const bool valid = r < n_valid && c < cb;
+            cp_async16_z(w_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4),
+                         valid ? Wt + (long long)(n0 + r) * K + (kc0 + c) * 8 : Wt, valid);
+        }
+    };
+    for (int j = 0; j < n_stages; ++j) {
+        if (j < nkb) fill(j);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = s_tmem_base;
+
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % n_stages;
+        const uint32_t a_st = smem0 + s * stage_bytes, w_st = a_st + A_STAGE_BYTES;
+        // groups committed so far: n_stages + kb ; block kb sits in group kb (kb < n_stages) or kb+1 -> allow n_stages-2 pending
+        if (n_stages >= 4) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (n_stages == 3) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (GATE) {
+            // each thread rescales exactly the chunks it copied itself
+            const int kc0 = kb * 8;
+            const int cb = min(8, kchunks - kc0), cbp = (cb + 1) & ~1;
+            if (GATE == 1) {
+                for (int idx = tid; idx < BM * cbp; idx += 128) {
+                    const int r = idx / cbp, c = idx - r * cbp;
+                    if (r < rows_valid && c < cb) {
+                        const uint32_t addr = a_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+                        const int cr = (m0 + r) / hw - crop0;
+                        sts128_(addr, scale8s<T>(lds128(addr), sG + (uint32_t)(cr * K + (kc0 + c) * 8) * 4));
+                    }
+                }
+            } else {
+                for (int idx = tid; idx < umma_n * cbp; idx += 128) {
+                    const int r = idx / cbp, c = idx - r * cbp;
+                    if (r < n_valid && c < cb) {
+                        const uint32_t addr = w_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+                        sts128_(addr, scale8s<T>(lds128(addr), sG + (uint32_t)((kc0 + c) * 8) * 4));
+                    }
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0 && !s_abort) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int krem = min(BK, K - kb * BK);
+            const int ksteps = (krem + 15) >> 4;
+            const uint64_t ad = make_desc(a_st), bd = make_desc(w_st);
+            for (int k = 0; k < ksteps; ++k)
+                umma_f16(tmem_d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            umma_commit(&mbar[s]);
+        }
+        // refill the stage block kb-1 used (its MMAs are done or about to be) with block kb-1+n_stages
+        if (kb >= 1 && kb - 1 + n_stages < nkb) {
+            const int pb = kb - 1;
+            if (!mbar_wait(&mbar[pb % n_stages], (pb / n_stages) & 1)) s_abort = 1;
+            fill(pb + n_stages);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    {
+        const int last = nkb - 1;
+        if (!mbar_wait(&mbar[last % n_stages], (last / n_stages) & 1)) s_abort = 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncthreads();
+
+    // ---- epilogue (as in pw_tc_kernel): TMEM -> +shift, swish, +residual -> 16-bit -> stage -> coalesced stores
+    const int nch = n_valid >> 3;
+    const int pitch16 = nch | 1;
+    uint4* stage = reinterpret_cast<uint4*>(smem_raw + (smem0 - smem_u32(smem_raw)));
+    const bool row_ok = tid < rows_valid;
+    const long long m = (long long)m0 + tid;
+    if (!s_abort) {
+        const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);
+        for (int c0 = 0; c0 < n_valid; c0 += 16) {
+            float v[16];
+            tmem_ld16(lane_base + (uint32_t)c0, v);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int n = n0 + c0 + h * 8;
+                if (c0 + h * 8 >= n_valid) break;
+                float o[8];
+                const float4 b0 = *reinterpret_cast<const float4*>(bias + n), b1 = *reinterpret_cast<const float4*>(bias + n + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float x = v[h * 8 + j] + bb[j];
+                    o[j] = SWISH ? swish_fast(x) : x;
+                }
+                if (RESID && row_ok) {
+                    float r[8];
+                    ld8<T>(resid + m * N + n, r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] += r[j];
+                }
+                st8<T>(reinterpret_cast<T*>(stage + tid * pitch16 + ((c0 >> 3) + h)), o);
+            }
+        }
+    }
+    __syncthreads();
+    if (!s_abort) {
+        for (int idx = tid; idx < rows_valid * nch; idx += 128) {
+            const int r = idx / nch, j = idx - r * nch;
+            *reinterpret_cast<uint4*>(out + ((long long)m0 + r) * N + n0 + j * 8) = stage[r * pitch16 + j];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)tmem_cols) : "memory");
+}
+
+template <typename T>
+int launch_pw_tc2(cudaStream_t stream, const T* A, const void* Wt16, const float* bias, const float* gate, const T* resid,
+                  T* out, long long M, int K, int N, int hw, bool swish) {
+    if (sizeof(T) != 2) return 1;
+    if ((K & 7) || (N & 7) || M > 0x7fffffffLL) return 1;
+    const bool per_crop = gate && hw >= 784;                 // gate on W, tiles stay inside a crop
+    const int tpc = (hw + BM - 1) / BM;
+    const long long m_tiles = per_crop ? (M / hw) * tpc : (M + BM - 1) / BM;
+    int n_tile = N;
+    if (N > 256) {
+        int parts = (N + 255) / 256;
+        while (true) {
+            n_tile = ((N + parts - 1) / parts + 15) & ~15;
+            if (n_tile <= 256) break;
+            ++parts;
+        }
+    }
+    while (n_tile > 48 && m_tiles * ((N + n_tile - 1) / n_tile) < 296) {
+        const int parts = (N + n_tile - 1) / n_tile + 1;
+        const int nt = ((N + parts - 1) / parts + 15) & ~15;
+        if (nt >= n_tile) break;
+        n_tile = nt;
+    }
+    const int umma_n = (n_tile + 15) & ~15;
+    int tmem_cols = 32;
+    while (tmem_cols < umma_n) tmem_cols <<= 1;
+    const uint32_t idesc = make_idesc(std::is_same<T, __nv_bfloat16>::value, umma_n);
+    const int nkb = (K + BK - 1) / BK;
+    const size_t stage_bytes = A_STAGE_BYTES + (size_t)umma_n * BK * 2;
+    const size_t gate_bytes = gate ? (size_t)(per_crop ? 1 : 4) * K * 4 : 0;
+    const size_t out_bytes = (size_t)BM * ((size_t)(n_tile >> 3) | 1) * 16;
+    int n_stages = nkb < 4 ? nkb : 4;
+    while (n_stages > 2 && n_stages * stage_bytes + gate_bytes > 108 * 1024) --n_stages;   // keep two CTAs per SM
+    size_t smem = n_stages * stage_bytes + gate_bytes;
+    if (smem < out_bytes) smem = out_bytes;
+    smem += 1024;
+    if (smem > 200 * 1024) return 1;
+    dim3 grid((unsigned)((N + n_tile - 1) / n_tile), (unsigned)m_tiles);
+    const T* W = reinterpret_cast<const T*>(Wt16);
+#define TC2(SW, GA, RE)                                                                                              \
+    do {                                                                                                             \
+        auto kfn = pw_tc2_kernel<T, SW, GA, RE>;                                                                     \
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1; \
+        kfn<<<grid, 128, smem, stream>>>(A, W, bias, gate, resid, out, (int)M, K, N, hw, n_tile, umma_n, tmem_cols, n_stages, tpc, idesc); \
+    } while (0)
+    if (swish && !gate && !resid) TC2(true, 0, false);
+    else if (!swish && !gate && !resid) TC2(false, 0, false);
+    else if (!swish && gate && !resid) { if (per_crop) TC2(false, 2, false); else TC2(false, 1, false); }
+    else if (!swish && gate && resid) { if (per_crop) TC2(false, 2, true); else TC2(false, 1, true); }
+    else return 1;
+#undef TC2
+    return 0;
+}
+
 inline int read_and_clear_timeout_flag() {
     int v = 0, z = 0;
     if (cudaMemcpyFromSymbol(&v, g_tc_timeout_flag, sizeof(int)) != cudaSuccess) return -1;

@@ -98,6 +98,7 @@ struct whenet_ctx {
     int use_tc = 0;         // tensor-core kernels for the 1x1 convs
     bool tc_used = false;   // a tcgen05 kernel ran since the last timeout-flag check
     int dw_variant = 1;     // 0 = one output per thread, 1 = register-blocked strips
+    int pw_variant = 2;     // tensor-core 1x1 kernel: 1 = register-staged 2-stage ring, 2 = cp.async ring + in-smem SE gate
     int stem_variant = 1;   // 0 = 4 threads / pixel straight from global, 1 = smem-tiled, weights in the constant bank
     whenet::StemParams stem_params{};
     int use_fused = 0;      // K1: expand + depthwise in one kernel (16-bit storage only; default on for bf16/fp16)
@@ -250,7 +251,8 @@ int launch_pw(whenet_ctx* c, const char* name, const T* A, const float* W, const
     Scope sc(c, name, bytes, flops);
     if constexpr (sizeof(T) == 2) {
         if (c->use_tc && Wt16) {
-            int rc = whenet::tc::launch_pw_tc<T>(c->stream, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish);
+            int rc = c->pw_variant == 2 ? whenet::tc::launch_pw_tc2<T>(c->stream, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish)
+                                        : whenet::tc::launch_pw_tc<T>(c->stream, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish);
             if (rc == 0) { CK(cudaGetLastError()); c->tc_used = true; return 0; }
             if (rc < 0) return fail(WHENET_ECUDA, "tensor-core 1x1 launch failed for %s (rc=%d)", name, rc);
             // rc > 0: shape not supported by the tensor-core kernel -> CUDA-core kernel below
@@ -804,7 +806,9 @@ int debug_conv_impl(whenet_ctx* c, int use_tc, const float* A, const float* W, c
     int rc;
     if (use_tc) {
         rc = 1;
-        if constexpr (sizeof(T) == 2) rc = whenet::tc::launch_pw_tc<T>(c->stream, dA, dWt, dB, dG, dR, dO, M, K, N, hw, swish != 0);
+        if constexpr (sizeof(T) == 2)
+            rc = use_tc == 2 ? whenet::tc::launch_pw_tc2<T>(c->stream, dA, dWt, dB, dG, dR, dO, M, K, N, hw, swish != 0)
+                             : whenet::tc::launch_pw_tc<T>(c->stream, dA, dWt, dB, dG, dR, dO, M, K, N, hw, swish != 0);
         if (rc == 0 && cudaGetLastError() != cudaSuccess) rc = -1;
         if (rc != 0) rc = fail(WHENET_EINVAL, "tensor-core family cannot run M=%lld K=%d N=%d (rc=%d)", M, K, N, rc);
         else c->tc_used = true;
@@ -876,6 +880,7 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!strcmp(key, "tensor_cores")) { c->use_tc = value && c->precision != WHENET_PRECISION_FP32; return 0; }
     if (!strcmp(key, "dw_variant")) { c->dw_variant = value; return 0; }
     if (!strcmp(key, "stem_variant")) { c->stem_variant = value; return 0; }
+    if (!strcmp(key, "pw_variant")) { c->pw_variant = value; return 0; }
     if (!strcmp(key, "fused")) { c->use_fused = value && c->precision != WHENET_PRECISION_FP32; return 0; }
     if (!strcmp(key, "fused_max_block")) { c->fused_max_block = value; return 0; }
     if (!strcmp(key, "chunk")) {

@@ -34,7 +34,7 @@ def net():
     m.close()
 
 
-@pytest.mark.parametrize("use_tc", [0, 1])
+@pytest.mark.parametrize("use_tc", [0, 1, 2])
 @pytest.mark.parametrize("K,N,kind", _layer_shapes())
 def test_conv1x1_shapes(net, use_tc, K, N, kind):
     rng = np.random.default_rng(K * 1000 + N)
@@ -49,7 +49,7 @@ def test_conv1x1_shapes(net, use_tc, K, N, kind):
         gate = rng.uniform(0.1, 1.0, ((M + hw - 1) // hw, K)).astype(np.float32)
     if kind == "project_res":
         resid = _bf16_round(rng.standard_normal((M, N)))
-    got = net.debug_conv1x1(A, W, bias, gate=gate, resid=resid, hw=hw, swish=swish, use_tc=bool(use_tc))
+    got = net.debug_conv1x1(A, W, bias, gate=gate, resid=resid, hw=hw, swish=swish, use_tc=use_tc)
     Ag = A.astype(np.float64)
     if gate is not None:
         Ag = Ag * np.repeat(gate, hw, axis=0)[:M]
@@ -65,6 +65,29 @@ def test_conv1x1_shapes(net, use_tc, K, N, kind):
     assert np.all(err <= tol), (K, N, kind, float(err.max()), int(np.argmax(err - tol)))
 
 
+@pytest.mark.parametrize("K,N,res", [(32, 16, False), (96, 24, False), (144, 24, True), (144, 40, False), (240, 40, True)])
+def test_conv1x1_per_crop_gate_on_weights(net, K, N, res):
+    """hw >= 784: the cp.async kernel tiles per crop and folds the SE gate into the W rows in shared memory."""
+    rng = np.random.default_rng(K + N)
+    hw, crops = 784, 3
+    M = hw * crops
+    A = _bf16_round(rng.standard_normal((M, K)))
+    W = _bf16_round(rng.standard_normal((K, N)) / np.sqrt(K))
+    bias = rng.standard_normal(N).astype(np.float32)
+    gate = rng.uniform(0.1, 1.0, (crops, K)).astype(np.float32)
+    resid = _bf16_round(rng.standard_normal((M, N))) if res else None
+    got = net.debug_conv1x1(A, W, bias, gate=gate, resid=resid, hw=hw, use_tc=2)
+    ref = np.empty((M, N))
+    for c in range(crops):
+        Wg = _bf16_round(W * gate[c][:, None]).astype(np.float64)       # the kernel rounds W*gate back to bf16
+        ref[c * hw:(c + 1) * hw] = A[c * hw:(c + 1) * hw].astype(np.float64) @ Wg + bias
+    if res:
+        ref = ref + resid
+    err = np.abs(got - ref)
+    tol = 2.0 ** -7 * np.abs(ref) + 2e-2
+    assert np.all(err <= tol), (K, N, float(err.max()))
+
+
 @pytest.mark.parametrize("M", [1, 127, 128, 129, 1000])
 def test_conv1x1_tc_row_tails(net, M):
     rng = np.random.default_rng(M)
@@ -72,6 +95,7 @@ def test_conv1x1_tc_row_tails(net, M):
     A = _bf16_round(rng.standard_normal((M, K)))
     W = _bf16_round(rng.standard_normal((K, N)) / np.sqrt(K))
     bias = np.zeros(N, np.float32)
-    a = net.debug_conv1x1(A, W, bias, use_tc=True)
-    b = net.debug_conv1x1(A, W, bias, use_tc=False)
-    assert np.abs(a - b).max() <= 2.0 ** -6 * max(1.0, np.abs(b).max())
+    b = net.debug_conv1x1(A, W, bias, use_tc=0)
+    for fam in (1, 2):
+        a = net.debug_conv1x1(A, W, bias, use_tc=fam)
+        assert np.abs(a - b).max() <= 2.0 ** -6 * max(1.0, np.abs(b).max())
