@@ -31,9 +31,10 @@ using tc::BM;
 
 struct K1Params {
     const void* in;        // T [N][Hin][Hin][Cin]
-    const void* wt_aug;    // T [Cexp][Cin+8]   BN-folded weights, K-major, columns Cin / Cin+1 = shift hi / lo, rest 0
-    const float* w_dw;     // [KS*KS][Cexp]     (BN-folded)
-    const float* b_dw;     // [Cexp]
+    // every K1 constant is pre-multiplied by 1/2 (exact): swish(x) = h + h*tanh(h) with h = x/2 then needs no multiply
+    const void* wt_aug;    // T [Cexp][Cin+8]   0.5 * BN-folded weights, K-major, columns Cin / Cin+1 = 0.5*shift hi / lo, rest 0
+    const float* w_dw;     // [KS*KS][Cexp]     0.5 * BN-folded depthwise weights
+    const float* b_dw;     // [Cexp]            0.5 * BN shift
     void* out;             // T [N][Ho][Ho][Cexp]
     float* partial;        // [N][tiles][Cexp]
     int Hin, Ho, Cin, Cexp, pad;
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
                             uint4 lo, hi;
                             if (e_inside[mt]) {
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] = swish_fast(v[j]);
+                                for (int j = 0; j < 16; ++j) v[j] = swish_from_half(v[j]);
                                 lo = make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
                                 hi = make_uint4(pack2<T>(v[8], v[9]), pack2<T>(v[10], v[11]), pack2<T>(v[12], v[13]), pack2<T>(v[14], v[15]));
                             } else {
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
                 for (int r = 0; r < R; ++r) {
                     if (oxl0 + r < p.TW && oy < p.Ho && tx0 + oxl0 + r < p.Ho) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) { acc[r][i] = swish_fast(acc[r][i]); sum[i] += acc[r][i]; }
+                        for (int i = 0; i < 4; ++i) { acc[r][i] = swish_from_half(acc[r][i]); sum[i] += acc[r][i]; }
                         uint2 o;
                         o.x = pack2<T>(acc[r][0], acc[r][1]);
                         o.y = pack2<T>(acc[r][2], acc[r][3]);
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
 // (<= 110 KB shared memory, <= 256 TMEM columns), then the most work per CTA.  Returns false when K1 cannot run it.
 inline bool plan_k1_candidate(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, bool is_bf16, int TH, int TW, int R, int CC,
                               K1Params* p, size_t* smem_out) {
-    if (Ho % TH || Ho % TW || Cexp % CC || TW % R) return false;
+    if (Ho % TH || Ho % TW || Cexp % CC) return false;
     p->Hin = Hin; p->Ho = Ho; p->Cin = Cin; p->Cexp = Cexp; p->pad = pad;
     p->TH = TH; p->TW = TW;
     p->IH = (TH - 1) * s + k; p->IW = (TW - 1) * s + k;
@@ -361,25 +362,26 @@ inline bool plan_k1_candidate(int Hin, int Ho, int Cin, int Cexp, int k, int s, 
     p->pitchE = CC * 2 + 16;
     p->PY = 256 / (CC / 4);
     if (p->PY < 1) return false;
-    const int spr = TW / R;
+    const int spr = (TW + R - 1) / R;         // a ragged last strip computes (and discards) up to R-1 extra outputs
     p->spr_log2 = spr == 1 ? 0 : spr == 2 ? 1 : spr == 4 ? 2 : -1;
     if (p->spr_log2 < 0) return false;
     p->idesc = tc::make_idesc(is_bf16, CC);
     p->smem_A = p->nkb * p->mtiles * BM * 128;
     p->smem_W = ((p->nkb * CC * 128) + 1023) & ~1023;
     p->smem_C = (((k * k + 1) * CC * 4) + 1023) & ~1023;
-    p->smem_E = (((p->IH * p->IW + 16) * p->pitchE) + 1023) & ~1023;
+    // slack rows: a ragged strip still LOADS the columns of its discarded outputs
+    p->smem_E = (((p->IH * p->IW + R * s + 16) * p->pitchE) + 1023) & ~1023;
     *smem_out = (size_t)p->smem_A + 2 * p->smem_W + 2 * p->smem_C + p->smem_E + (size_t)p->PY * CC * 4 + 1024;
     return *smem_out <= 200 * 1024;
 }
 
 inline bool plan_k1(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, bool is_bf16, K1Params* p, int* R_out, size_t* smem_out) {
     struct Cand { int th, tw, r; };
-    const Cand s1[] = {{14, 14, 7}, {7, 14, 7}, {7, 7, 7}};
-    const Cand s2k3[] = {{8, 8, 4}, {7, 7, 7}};
-    const Cand s2[] = {{7, 7, 7}};
+    const Cand s1[] = {{14, 14, 7}, {7, 14, 7}, {7, 7, 7}, {7, 7, 4}};
+    const Cand s2k3[] = {{8, 8, 4}, {7, 7, 7}, {7, 7, 4}};
+    const Cand s2[] = {{7, 7, 7}, {7, 7, 4}};
     const Cand* cands = s == 1 ? s1 : (k == 3 ? s2k3 : s2);
-    const int ncand = s == 1 ? 3 : (k == 3 ? 2 : 1);
+    const int ncand = s == 1 ? 4 : (k == 3 ? 3 : 2);
     bool found = false;
     double best = -1;
     for (int i = 0; i < ncand; ++i)
@@ -388,11 +390,19 @@ inline bool plan_k1(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, b
             size_t smem = 0;
             if (!plan_k1_candidate(Hin, Ho, Cin, Cexp, k, s, pad, is_bf16, cands[i].th, cands[i].tw, cands[i].r, cc, &q, &smem)) continue;
             const bool two = smem <= 110 * 1024 && q.tmem_cols <= 256;
-            // score: co-residency first, then depthwise work items per chunk (parallelism inside the CTA)
-            const double items = (double)(cands[i].th * (cands[i].tw / cands[i].r)) * (cc / 4);
-            // few chunks matter too: every chunk costs three CTA-wide barriers
-            const double score = (two ? 300 : 0) + (items > 512 ? 512 : items) - 6.0 * q.n_chunks;
-            if (score > best) { best = score; *p = q; *R_out = cands[i].r; *smem_out = smem; found = true; }
+            // rough thread-instruction model of one CTA (constants from the ncu source view of round 1):
+            //   A fill ~20 / (pixel, chunk); per chunk: epilogue-1 ~4 / E element, depthwise ~1.8 x FMA count over
+            //   whole rounds of the 256 threads, ~400 / thread of barrier + prefetch overhead
+            const int R = cands[i].r, th = cands[i].th, tw = cands[i].tw;
+            const double items = (double)(th * ((tw + R - 1) / R)) * (cc / 4);
+            const double lanes = (double)q.PY * (cc / 4);
+            const double rounds = (double)(long long)((items + lanes - 1) / lanes);
+            const double epi = (double)q.IH * q.IW * cc * 4.0;
+            const double dw = rounds * 256.0 * R * k * k * 4 * 1.8;
+            const double per_cta = (double)q.IH * q.IW * (Cin / 8) * 20.0 + q.n_chunks * (epi + dw + 256.0 * 400.0);
+            double cost = per_cta / ((double)th * tw * Cexp);
+            if (!two) cost *= 1.4;
+            if (best < 0 || cost < best) { best = cost; *p = q; *R_out = R; *smem_out = smem; found = true; }
         }
     return found;
 }
@@ -412,6 +422,9 @@ int launch_k1(cudaStream_t stream, const K1Params& p, int k, int s, int R, size_
     if (k == 5 && s == 1 && R == 7) K1(5, 1, 7);
     if (k == 5 && s == 2 && R == 7) K1(5, 2, 7);
     if (k == 3 && s == 2 && R == 7) K1(3, 2, 7);
+    if (k == 3 && s == 1 && R == 4) K1(3, 1, 4);
+    if (k == 5 && s == 1 && R == 4) K1(5, 1, 4);
+    if (k == 5 && s == 2 && R == 4) K1(5, 2, 4);
 #undef K1
     return 1;
 }

@@ -119,6 +119,13 @@ __device__ __forceinline__ float swish_fast(float x) {
     return fmaf(h, t, h);
 }
 
+// same, for an argument that is ALREADY x/2 (the producer folded the 1/2 into its weights and shift)
+__device__ __forceinline__ float swish_from_half(float h) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+
 // ----------------------------------------------------------------------------- stem
 // out[n,oy,ox,co] = swish( bias[co] + sum_{ky,kx,ci} w[ky,kx,ci,co] * norm(in[n,2oy+ky,2ox+kx,ci]) )
 // TF SAME for 224/k3/s2: pad_before 0, pad_after 1 -> the taps at index 224 read zero

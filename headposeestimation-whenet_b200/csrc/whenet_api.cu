@@ -83,7 +83,8 @@ struct BlockW {   // device pointers into the fp32 arena
     float *w_se2 = nullptr, *b_se2 = nullptr;     // [cse][cexp], [cexp]
     float *w_proj = nullptr, *b_proj = nullptr;   // [cexp][cout], [cout]
     void *wt_exp = nullptr, *wt_proj = nullptr;   // 16-bit [N][K] copies for the tensor-core path
-    void* wt_exp_aug = nullptr;                   // 16-bit [cexp][cin+8]: weights | shift_hi | shift_lo | 0... (K1)
+    void* wt_exp_aug = nullptr;                   // 16-bit [cexp][cin+8]: 0.5*(weights | shift_hi | shift_lo) | 0... (K1)
+    float *w_dw_h = nullptr, *b_dw_h = nullptr;   // 0.5 * depthwise weights / shift (K1)
 };
 
 struct K1Plan { bool valid = false; whenet::fused::K1Params p{}; int R = 0; size_t smem = 0; };
@@ -332,7 +333,7 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
         if constexpr (sizeof(T) == 2) {
             if (c->use_fused && c->k1[i].valid && b.idx <= c->fused_max_block) {
                 whenet::fused::K1Params p = c->k1[i].p;
-                p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw; p.b_dw = w.b_dw; p.out = D; p.partial = c->d_partial;
+                p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial;
                 snprintf(nm, sizeof nm, "b%02d.k1", b.idx);
                 Scope sc(c, nm, (double)nb * ((double)b.hin * b.hin * b.cin + (double)b.hout * b.hout * b.cexp) * sizeof(T),
                          2.0 * nb * ((double)b.hin * b.hin * b.cin * b.cexp + (double)b.hout * b.hout * b.k * b.k * b.cexp));
@@ -562,7 +563,7 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
                                                   while (arena.size() % 4) arena.push_back(0.f); return off; };
     auto put16 = [&](const std::vector<float>& v) { size_t off = arena16src.size(); arena16src.insert(arena16src.end(), v.begin(), v.end());
                                                     while (arena16src.size() % 8) arena16src.push_back(0.f); return off; };
-    struct Off { size_t w_exp, b_exp, w_dw, b_dw, w_se1t, b_se1, w_se2, b_se2, w_proj, b_proj, t_exp, t_proj, t_aug; };
+    struct Off { size_t w_exp, b_exp, w_dw, b_dw, w_se1t, b_se1, w_se2, b_se2, w_proj, b_proj, t_exp, t_proj, t_aug, w_dw_h, b_dw_h; };
     // values of the augmented expand weights; shift columns are filled after 16-bit rounding of the high part
     std::vector<std::pair<size_t, float>> shift_lo_fix;   // (index in arena16src of the hi column, full-precision shift)
     std::vector<Off> offs(c->blocks.size());
@@ -619,11 +620,11 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
             const int ka = b.cin + 8;
             std::vector<float> aug((size_t)b.cexp * ka, 0.f);
             for (int n = 0; n < b.cexp; ++n) {
-                for (int k = 0; k < b.cin; ++k) aug[(size_t)n * ka + k] = arena16src[o.t_exp + (size_t)n * b.cin + k];
-                aug[(size_t)n * ka + b.cin] = arena[o.b_exp + n];
+                for (int k = 0; k < b.cin; ++k) aug[(size_t)n * ka + k] = 0.5f * arena16src[o.t_exp + (size_t)n * b.cin + k];
+                aug[(size_t)n * ka + b.cin] = 0.5f * arena[o.b_exp + n];
             }
             o.t_aug = put16(aug);
-            for (int n = 0; n < b.cexp; ++n) shift_lo_fix.push_back({o.t_aug + (size_t)n * ka + b.cin, arena[o.b_exp + n]});
+            for (int n = 0; n < b.cexp; ++n) shift_lo_fix.push_back({o.t_aug + (size_t)n * ka + b.cin, 0.5f * arena[o.b_exp + n]});
         }
         {
             const std::string nm = "depthwise_conv2d_" + std::to_string(++dwc);
@@ -635,6 +636,9 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
                 for (int ch = 0; ch < b.cexp; ++ch) w[(size_t)tap * b.cexp + ch] = (float)((double)t->data[(size_t)tap * b.cexp + ch] * f.scale[ch]);
             for (int ch = 0; ch < b.cexp; ++ch) bb[ch] = (float)f.shift[ch];
             o.w_dw = put(w); o.b_dw = put(bb);
+            for (float& v : w) v *= 0.5f;
+            for (float& v : bb) v *= 0.5f;
+            o.w_dw_h = put(w); o.b_dw_h = put(bb);
         }
         {
             const std::string n1 = conv_name();
@@ -709,6 +713,7 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
             w.wt_exp_aug = base16 ? base16 + o.t_aug * 2 : nullptr;
         }
         w.w_dw = A + o.w_dw; w.b_dw = A + o.b_dw;
+        w.w_dw_h = A + o.w_dw_h; w.b_dw_h = A + o.b_dw_h;
         w.w_se1t = A + o.w_se1t; w.b_se1 = A + o.b_se1; w.w_se2 = A + o.w_se2; w.b_se2 = A + o.b_se2;
         w.w_proj = A + o.w_proj; w.b_proj = A + o.b_proj;
         w.wt_proj = base16 ? base16 + o.t_proj * 2 : nullptr;
@@ -841,6 +846,25 @@ int whenet_debug_conv1x1(whenet_ctx* c, int use_tc, const float* A, const float*
         case WHENET_PRECISION_FP16: return debug_conv_impl<__half>(c, use_tc, A, W, bias, gate, resid, out, M, K, N, hw, swish);
     }
     return fail(WHENET_EINVAL, "bad precision");
+}
+
+int whenet_debug_set_k1_plan(whenet_ctx* c, int block, int th, int tw, int r, int cc) {
+    if (!c || block < 2 || block > (int)c->blocks.size()) return fail(WHENET_EINVAL, "bad block index");
+    if (c->precision == WHENET_PRECISION_FP32) return fail(WHENET_EINVAL, "K1 needs a 16-bit storage mode");
+    const BlockCfg& b = c->blocks[block - 1];
+    if (cc < 16 || cc > 128 || (cc & 15) || r < 1 || th < 1 || tw < 1) return fail(WHENET_EINVAL, "bad plan parameters");
+    if (!((b.k == 3 && b.s == 2 && (r == 4 || r == 7)) || (b.k == 3 && b.s == 1 && (r == 7 || r == 4)) ||
+          (b.k == 5 && b.s == 1 && (r == 7 || r == 4)) || (b.k == 5 && b.s == 2 && (r == 7 || r == 4))))
+        return fail(WHENET_EINVAL, "no K1 instantiation for k=%d s=%d r=%d", b.k, b.s, r);
+    K1Plan pl;
+    if (!whenet::fused::plan_k1_candidate(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, c->precision == WHENET_PRECISION_BF16,
+                                          th, tw, r, cc, &pl.p, &pl.smem))
+        return fail(WHENET_EINVAL, "plan %dx%d r%d cc%d does not fit block %d", th, tw, r, cc, block);
+    pl.valid = true;
+    pl.R = r;
+    c->k1[block - 1] = pl;
+    free_ws(c);      // the squeeze-partials buffer depends on the tile count
+    return 0;
 }
 
 int whenet_profile_enable(whenet_ctx* c, int enable) {
