@@ -195,8 +195,6 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
         e_row[mt] = sE + (uint32_t)r * p.pitchE;
     }
     const int units = p.CC >> 4;
-    const int u0 = (warp >> 2) ? (units + 1) / 2 : 0;
-    const int u1 = (warp >> 2) ? units : (units + 1) / 2;
     // depthwise: thread = (4-channel vector cv, strip lane py)
     const int CVc = p.CC >> 2;
     const int py = tid / CVc, cv = tid - py * CVc;
@@ -240,11 +238,13 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
         const bool ok = !s_abort;
 
         // ---- epilogue 1: TMEM -> swish -> E (16-bit).  The BN shift is already in the accumulator.
+        //      (M tile, 16-column unit) pairs alternate between the two warp halves so both carry the same load.
         if (ok) {
+            const int half = warp >> 2;
 #pragma unroll
             for (int mt = 0; mt < 3; ++mt) {
                 if (mt < p.mtiles) {
-                    for (int u = u0; u < u1; ++u) {
+                    for (int u = (mt * units + half) & 1; u < units; u += 2) {
                         float v[16];
                         tc::tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mt * p.CC + u * 16), v);
                         if (e_valid[mt]) {
@@ -326,13 +326,14 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
                          "f"(sum[0]), "f"(sum[1]), "f"(sum[2]), "f"(sum[3]) : "memory");
         }
         __syncthreads();
-        if (ok && dw_active && py == 0) {
-            float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && tid < p.CC) {
+            float tot = 0.f;
             for (int y = 0; y < p.PY; ++y) {
-                const float4 t = lds_f4(sR + (uint32_t)(y * p.CC + cv * 4) * 4);
-                tot.x += t.x; tot.y += t.y; tot.z += t.z; tot.w += t.w;
+                float t;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(sR + (uint32_t)(y * p.CC + tid) * 4));
+                tot += t;
             }
-            *reinterpret_cast<float4*>(p.partial + ((long long)n * gridDim.x + tile) * p.Cexp + cbase + cv * 4) = tot;
+            p.partial[((long long)n * gridDim.x + tile) * p.Cexp + cbase + tid] = tot;
         }
         // E, the squeeze scratch and TMEM are reused only after the barrier at the top of the next chunk
     }
@@ -382,6 +383,15 @@ inline bool plan_k1(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, b
     const Cand s2[] = {{7, 7, 7}, {7, 7, 4}};
     const Cand* cands = s == 1 ? s1 : (k == 3 ? s2k3 : s2);
     const int ncand = s == 1 ? 4 : (k == 3 ? 3 : 2);
+    // plans measured fastest on B200 by tools/tune_k1.py (round 1) where they differ from the model's pick
+    if (s == 1 && k == 5 && (Hin == 28 || Hin == 14) && Cexp % 48 == 0) {
+        K1Params q{};
+        size_t smem = 0;
+        if (plan_k1_candidate(Hin, Ho, Cin, Cexp, k, s, pad, is_bf16, 14, 14, 7, 48, &q, &smem)) {
+            *p = q; *R_out = 7; *smem_out = smem;
+            return true;
+        }
+    }
     bool found = false;
     double best = -1;
     for (int i = 0; i < ncand; ++i)

@@ -88,6 +88,13 @@ struct BlockW {   // device pointers into the fp32 arena
 };
 
 struct K1Plan { bool valid = false; whenet::fused::K1Params p{}; int R = 0; size_t smem = 0; };
+struct GraphKey {
+    int n, in_u8, sig;
+    const void* in;
+    float *ang, *log;
+    bool operator==(const GraphKey& o) const { return n == o.n && in_u8 == o.in_u8 && sig == o.sig && in == o.in && ang == o.ang && log == o.log; }
+};
+struct GraphEntry { GraphKey key; cudaGraphExec_t exec; int launches; };
 struct EvPair { cudaEvent_t a, b; int stat; };
 struct Stat { std::string name; double bytes = 0, flops = 0; int launches = 0; float ms = 0; };
 
@@ -102,6 +109,8 @@ struct whenet_ctx {
     int pw_variant = 2;     // tensor-core 1x1 kernel: 1 = register-staged 2-stage ring, 2 = cp.async ring + in-smem SE gate
     int stem_variant = 1;   // 0 = 4 threads / pixel straight from global, 1 = smem-tiled, weights in the constant bank
     whenet::StemParams stem_params{};
+    int use_graph = 0;      // replay device-resident forwards from a captured CUDA graph (small-batch latency)
+    std::vector<GraphEntry> graphs;
     int use_fused = 0;      // K1: expand + depthwise in one kernel (16-bit storage only; default on for bf16/fp16)
     int fused_max_block = 16;  // blocks 2..fused_max_block use K1
     std::vector<K1Plan> k1;
@@ -204,7 +213,9 @@ int add_tap<float>(whenet_ctx* c, const std::string& name, const float* src, siz
 }
 
 // ----------------------------------------------------------------------------- workspace
+void drop_graphs(whenet_ctx* c);
 void free_ws(whenet_ctx* c) {
+    drop_graphs(c);
     for (void** p : {&c->bufA, &c->bufB, &c->bufE, &c->bufD, &c->d_in[0], &c->d_in[1]}) {
         if (*p) cudaFree(*p);
         *p = nullptr;
@@ -393,6 +404,15 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
     return 0;
 }
 
+void drop_graphs(whenet_ctx* c) {
+    for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
+}
+
+int options_signature(const whenet_ctx* c) {
+    return c->chunk * 1000003 + c->use_tc * 64 + c->dw_variant * 32 + c->use_fused * 16 + c->stem_variant * 8 + c->pw_variant * 2 + c->fused_max_block * 128;
+}
+
 template <typename T, bool IN_U8>
 int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* angles_out, float* logits_out, int out_is_device) {
     int rc = ensure_ws(c);
@@ -400,6 +420,20 @@ int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* a
     const size_t in_es = IN_U8 ? 1 : 4;
     float* d_ang = out_is_device ? angles_out : c->d_angles;
     float* d_log = logits_out ? (out_is_device ? logits_out : c->d_logits) : nullptr;
+    // ---- device-resident forwards can be replayed from a captured graph (66 -> 1 launch; small-batch latency)
+    const bool graphable = c->use_graph && in_is_device && out_is_device && !c->prof_on && !c->taps_on;
+    GraphKey key{n, IN_U8 ? 1 : 0, options_signature(c), in, d_ang, d_log};
+    if (graphable) {
+        for (auto& g : c->graphs)
+            if (g.key == key) {
+                CK(cudaGraphLaunch(g.exec, c->stream));
+                c->launches += g.launches;
+                c->tc_used = true;
+                return 0;
+            }
+        CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    }
+    const int64_t launches0 = c->launches;
     int ci = 0;
     for (int off = 0; off < n; off += c->chunk, ++ci) {
         const int nb = std::min(c->chunk, n - off);
@@ -418,8 +452,23 @@ int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* a
         }
         rc = forward_chunk<T, IN_U8>(c, d_in, nb, d_ang + (size_t)off * 3, d_log ? d_log + (size_t)off * WHENET_N_LOGITS : nullptr,
                                      c->taps_on && off == 0 && nb <= 8);
-        if (rc) return rc;
+        if (rc) {
+            if (graphable) { cudaGraph_t g = nullptr; cudaStreamEndCapture(c->stream, &g); if (g) cudaGraphDestroy(g); }
+            return rc;
+        }
         if (!in_is_device) CK(cudaEventRecord(c->ev_free[slot], c->stream));
+    }
+    if (graphable) {
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamEndCapture(c->stream, &graph));
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(WHENET_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+        if (c->graphs.size() >= 8) { cudaGraphExecDestroy(c->graphs.front().exec); c->graphs.erase(c->graphs.begin()); }
+        c->graphs.push_back({key, exec, (int)(c->launches - launches0)});
+        CK(cudaGraphLaunch(exec, c->stream));
+        return 0;
     }
     if (!out_is_device) {
         CK(cudaMemcpyAsync(angles_out, c->d_angles, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -721,13 +770,14 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
     c->w_head = A + o_whead; c->b_head = A + o_bhead; c->wt_head = base16 ? base16 + o_thead * 2 : nullptr;
     c->w_fct = A + o_wfct; c->b_fc = A + o_bfc;
     c->weights_loaded = true;
+    drop_graphs(c);
     return 0;
 }
 
 int whenet_set_stream(whenet_ctx* c, void* s) {
     if (!c) return fail(WHENET_EINVAL, "null context");
     c->stream = s ? (cudaStream_t)s : c->own_stream;
-    return 0;
+    return 0;   // captured graphs are stream independent: they are launched on whatever stream is current
 }
 
 int whenet_forward_u8(whenet_ctx* c, const uint8_t* in, int n, int in_is_device, float* angles, float* logits, int out_is_device) {
@@ -902,6 +952,7 @@ int64_t whenet_launch_count(whenet_ctx* c) { return c ? c->launches : 0; }
 int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!c || !key) return fail(WHENET_EINVAL, "bad arguments");
     if (!strcmp(key, "tensor_cores")) { c->use_tc = value && c->precision != WHENET_PRECISION_FP32; return 0; }
+    if (!strcmp(key, "graph")) { c->use_graph = value; if (!value) drop_graphs(c); return 0; }
     if (!strcmp(key, "dw_variant")) { c->dw_variant = value; return 0; }
     if (!strcmp(key, "stem_variant")) { c->stem_variant = value; return 0; }
     if (!strcmp(key, "pw_variant")) { c->pw_variant = value; return 0; }
@@ -919,6 +970,7 @@ void whenet_destroy(whenet_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    drop_graphs(c);
     free_ws(c);
     for (auto& kv : c->taps) cudaFree(kv.second.first);
     for (auto& p : c->ev_used) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }

@@ -270,6 +270,35 @@ def test_empty_batch(net32):
     assert y.shape == (0,) and y.dtype == np.float32
 
 
+def test_cuda_graph_replay(sample_crops, jitter_crops):
+    """Device-resident forwards replayed from a captured CUDA graph give bit-identical results, also after the
+    input buffer CONTENT changes (same addresses), and new shapes capture new graphs."""
+    import torch
+    import whenet_b200
+    m = whenet_b200.WHENet(SNAP, device=0, precision="bf16", max_batch=8)
+    crops = np.concatenate([sample_crops, jitter_crops])
+    ref = np.stack(m.get_angle(crops), axis=1)
+    s = torch.cuda.Stream()
+    torch.cuda.set_stream(s)
+    m.set_stream(s.cuda_stream)
+    m.set_option("graph", 1)
+    x = torch.from_numpy(crops).cuda()
+    y = torch.empty((8, 3), dtype=torch.float32, device="cuda")
+    for _ in range(3):
+        m.forward_device(x, y)
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy(), ref)
+    x.copy_(torch.from_numpy(crops[::-1].copy()).cuda())
+    m.forward_device(x, y)
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy(), ref[::-1])
+    m.forward_device(x[:3], y[:3])
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy()[:3], ref[::-1][:3])
+    torch.cuda.set_stream(torch.cuda.default_stream())
+    m.close()
+
+
 def test_device_resident_async(sample_crops):
     import torch
     import whenet_b200
