@@ -19,6 +19,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_fused.cuh"
+#include "kernels_crop.cuh"
 
 namespace {
 
@@ -129,6 +130,9 @@ struct whenet_ctx {
     float *d_partial = nullptr, *d_gate = nullptr, *d_angles = nullptr, *d_logits = nullptr, *d_pooled = nullptr;
     void* d_in[2] = {nullptr, nullptr};
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    // crop front-end staging
+    uint8_t* d_frame = nullptr; size_t frame_cap = 0;
+    int4* d_rects = nullptr; int rects_cap = 0;
     // taps
     bool taps_on = false;
     std::map<std::string, std::pair<float*, size_t>> taps;
@@ -788,6 +792,44 @@ int whenet_forward_f32(whenet_ctx* c, const float* in, int n, int in_is_device, 
     return forward_dispatch<false>(c, in, n, in_is_device, angles, logits, out_is_device);
 }
 
+int whenet_crop_resize_u8(whenet_ctx* c, const uint8_t* frame, int H, int W, int frame_is_device,
+                          const int32_t* rects, int m, int swap_rb, uint8_t* crops_out) {
+    if (!c || !frame || !rects || !crops_out) return fail(WHENET_EINVAL, "null argument");
+    if (H < 1 || W < 1 || m < 1) return fail(WHENET_EINVAL, "bad frame size or box count");
+    for (int i = 0; i < m; ++i) {
+        const int32_t* r = rects + 4 * i;
+        if (!(0 <= r[0] && r[0] < r[1] && r[1] <= H && 0 <= r[2] && r[2] < r[3] && r[3] <= W))
+            return fail(WHENET_EINVAL, "box %d: slice [%d:%d, %d:%d] is empty or outside the %dx%d frame (cv2.resize would raise)",
+                        i, r[0], r[1], r[2], r[3], H, W);
+    }
+    CK(cudaSetDevice(c->device));
+    const uint8_t* d_frame = frame;
+    if (!frame_is_device) {
+        const size_t bytes = (size_t)H * W * 3;
+        if (c->frame_cap < bytes) {
+            if (c->d_frame) cudaFree(c->d_frame);
+            c->d_frame = nullptr; c->frame_cap = 0;
+            CK(cudaMalloc(&c->d_frame, bytes));
+            c->frame_cap = bytes;
+        }
+        CK(cudaMemcpyAsync(c->d_frame, frame, bytes, cudaMemcpyHostToDevice, c->stream));
+        d_frame = c->d_frame;
+    }
+    if (c->rects_cap < m) {
+        if (c->d_rects) cudaFree(c->d_rects);
+        c->d_rects = nullptr; c->rects_cap = 0;
+        CK(cudaMalloc(&c->d_rects, (size_t)m * sizeof(int4)));
+        c->rects_cap = m;
+    }
+    CK(cudaMemcpyAsync(c->d_rects, rects, (size_t)m * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+    {
+        Scope sc(c, "crop_resize", (double)m * 224 * 224 * 3 * 2, 0.0);
+        whenet::crop_resize_kernel<<<dim3((224 * 224 + 255) / 256, m), 256, 0, c->stream>>>(d_frame, H, W, c->d_rects, crops_out, swap_rb);
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
 int whenet_synchronize(whenet_ctx* c) {
     if (!c) return fail(WHENET_EINVAL, "null context");
     CK(cudaSetDevice(c->device));
@@ -972,6 +1014,8 @@ void whenet_destroy(whenet_ctx* c) {
     cudaDeviceSynchronize();
     drop_graphs(c);
     free_ws(c);
+    if (c->d_frame) cudaFree(c->d_frame);
+    if (c->d_rects) cudaFree(c->d_rects);
     for (auto& kv : c->taps) cudaFree(kv.second.first);
     for (auto& p : c->ev_used) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);

@@ -19,7 +19,7 @@ from typing import Optional
 
 import numpy as np
 
-from . import _lib, arch, weights as _weights
+from . import _lib, arch, crops as _crops, weights as _weights
 from ._lib import WhenetError, check
 
 
@@ -169,6 +169,32 @@ class WHENet:
         """Host buffers (numpy or pinned tensors) in, host buffers out; synchronous."""
         n = int(crops_u8.shape[0]) if n is None else int(n)
         check(self._L.whenet_forward_u8(self._h, _ptr(crops_u8), n, 0, _ptr(angles_out), _ptr(logits_out), 0))
+
+    def get_angle_from_frame(self, frame_bgr, boxes, margin: bool = True, return_crops: bool = False):
+        """Stream path (reference demo_video.py:11-28 for ALL heads of a frame in one batch): ``frame_bgr`` is the
+        H x W x 3 uint8 frame as cv2 delivers it, ``boxes`` the detector output (M,4) = (y_min, x_min, y_max, x_max).
+        Crops are cut, colour-swapped and resized on the GPU (bit-identical to cv2.resize) and never visit the host."""
+        import torch
+        frame = np.ascontiguousarray(frame_bgr, dtype=np.uint8)
+        if frame.ndim != 3 or frame.shape[2] != 3:
+            raise ValueError("frame must be H x W x 3 uint8")
+        rects = _crops.rects_from_boxes(boxes, frame.shape[0], frame.shape[1], margin)
+        m = rects.shape[0]
+        if m == 0:
+            z = np.zeros((0,), dtype=np.float32)
+            return z, z.copy(), z.copy()
+        with torch.cuda.device(self.device):
+            d_crops = torch.empty((m, 224, 224, 3), dtype=torch.uint8, device="cuda")
+            d_ang = torch.empty((m, 3), dtype=torch.float32, device="cuda")
+            check(self._L.whenet_crop_resize_u8(self._h, _ptr(frame), frame.shape[0], frame.shape[1], 0,
+                                                _ptr(rects), m, 1, _ptr(d_crops)))
+            for off in range(0, m, self.max_batch):
+                nb = min(self.max_batch, m - off)
+                check(self._L.whenet_forward_u8(self._h, _ptr(d_crops[off:off + nb]), nb, 1, _ptr(d_ang[off:off + nb]), None, 1))
+            self.synchronize()
+            ang = d_ang.cpu().numpy()
+            out = (ang[:, 0].copy(), ang[:, 1].copy(), ang[:, 2].copy())
+            return out + (d_crops.cpu().numpy(),) if return_crops else out
 
     def set_stream(self, stream_ptr: Optional[int]):
         """Run on a caller-owned CUDA stream.  ``0`` (torch's default stream) is passed as

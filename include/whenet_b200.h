@@ -94,6 +94,16 @@ int whenet_forward_u8(whenet_ctx* ctx, const uint8_t* nhwc_rgb, int n, int in_is
 int whenet_forward_f32(whenet_ctx* ctx, const float* nhwc_normalised, int n, int in_is_device,
                        float* angles_out, float* logits_out, int out_is_device);
 
+/* Crop front-end of the stream path; replaces, for ALL heads of a frame at once, the per-head
+ * slice + cv2.cvtColor(BGR2RGB) + cv2.resize(.., (224,224)) of reference demo_video.py:21-23 (and demo.py:10-11).
+ * `frame`: H x W x 3 uint8 (host, or device when frame_is_device); `rects`: m x 4 int32 host array of slice
+ * bounds (y0, y1, x0, x1) with 0 <= y0 < y1 <= H, 0 <= x0 < x1 <= W (the margin arithmetic of
+ * demo_video.py:13-19 is host-side, see whenet_b200/crops.py); `swap_rb` != 0 converts BGR -> RGB.
+ * `crops_out`: m x 224 x 224 x 3 uint8 in DEVICE memory (feed it to whenet_forward_u8 with in_is_device=1),
+ * bit-identical to OpenCV's 8-bit INTER_LINEAR resize.  Asynchronous on the context's stream. */
+int whenet_crop_resize_u8(whenet_ctx* ctx, const uint8_t* frame, int H, int W, int frame_is_device,
+                          const int32_t* rects, int m, int swap_rb, uint8_t* crops_out);
+
 /* Block until everything queued by this context has finished. */
 int whenet_synchronize(whenet_ctx* ctx);
 
