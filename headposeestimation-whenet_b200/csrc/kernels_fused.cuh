@@ -37,6 +37,11 @@ struct K1Params {
     const float* b_dw;     // [Cexp]            0.5 * BN shift
     void* out;             // T [N][Ho][Ho][Cexp]
     float* partial;        // [N][tiles][Cexp]
+    // SE excite, run by the last CTA of each crop to finish (se_counter == nullptr: left to se_gate_kernel)
+    const float *w_se1t, *b_se1, *w_se2, *b_se2;
+    float* gate;           // [N][Cexp]
+    int* se_counter;       // [N], zero on entry, self-resetting
+    int Cse;
     int Hin, Ho, Cin, Cexp, pad;
     int TH, TW, IH, IW;    // output tile, input halo tile
     int tiles_x, tiles_y;
@@ -100,6 +105,7 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_abort;
+    __shared__ int s_last;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -338,9 +344,26 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
         // E, the squeeze scratch and TMEM are reused only after the barrier at the top of the next chunk
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __threadfence();                       // this CTA's squeeze partials are visible device-wide before the ticket
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)p.tmem_cols) : "memory");
+
+    // ---- SE excite by the last CTA of this crop (classic fence + ticket pattern; the sums stay in fixed order)
+    if (p.se_counter) {
+        if (tid == 0) {
+            const int ticket = atomicAdd(p.se_counter + n, 1);
+            s_last = ticket == (int)gridDim.x - 1;
+            if (s_last) p.se_counter[n] = 0;
+        }
+        __syncthreads();
+        if (s_last && !s_abort) {
+            __threadfence();
+            float* sm = reinterpret_cast<float*>(smem_raw + (sE - tc::smem_u32(smem_raw)));    // E is free now
+            se_gate_crop(p.partial + (long long)n * gridDim.x * p.Cexp, (int)gridDim.x, 1.0f / (float)(p.Ho * p.Ho),
+                         p.w_se1t, p.b_se1, p.w_se2, p.b_se2, p.gate + (long long)n * p.Cexp, p.Cexp, p.Cse, sm);
+        }
+    }
 }
 
 // Tile plan for one block: try a few tile shapes x chunk widths, prefer plans that let two CTAs share an SM

@@ -495,20 +495,19 @@ __global__ void __launch_bounds__(256) dw_strip_kernel(const T* __restrict__ in,
 
 // ----------------------------------------------------------------------------- SE gate
 // mean[c] = sum_tiles partial / (Ho*Ho); h = swish(W1^T mean + b1); gate = sigmoid(W2^T h + b2)
-__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ partial, int tiles, float inv_hw,
-                                                      const float* __restrict__ w1t,  // [Cse][C]
-                                                      const float* __restrict__ b1,   // [Cse]
-                                                      const float* __restrict__ w2,   // [Cse][C]
-                                                      const float* __restrict__ b2,   // [C]
-                                                      float* __restrict__ gate,       // [N][C]
-                                                      int C, int Cse) {
-    extern __shared__ float sm[];   // mean[C] | hid[Cse]
+// Device function for ONE crop, executed by a whole 256-thread CTA: the stand-alone kernel below and the tail of
+// K1 (the last CTA of a crop to finish) both call it.  `sm` = C + Cse floats of shared memory.
+// `partial` is read with ld.global.cg: it may have been written by other CTAs of the same launch.
+__device__ __forceinline__ void se_gate_crop(const float* __restrict__ partial_n, int tiles, float inv_hw,
+                                             const float* __restrict__ w1t, const float* __restrict__ b1,
+                                             const float* __restrict__ w2, const float* __restrict__ b2,
+                                             float* __restrict__ gate_n, int C, int Cse, float* sm) {
     float* mean = sm;
     float* hid = sm + C;
-    const int n = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     for (int c = tid; c < C; c += 256) {
         float s = 0.f;
-        for (int t = 0; t < tiles; ++t) s += partial[((long long)n * tiles + t) * C + c];
+        for (int t = 0; t < tiles; ++t) s += __ldcg(partial_n + (long long)t * C + c);
         mean[c] = s * inv_hw;
     }
     __syncthreads();
@@ -524,8 +523,20 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
     for (int c = tid; c < C; c += 256) {
         float s = b2[c];
         for (int j = 0; j < Cse; ++j) s = fmaf(hid[j], w2[(long long)j * C + c], s);
-        gate[(long long)n * C + c] = sigmoid_f(s);
+        gate_n[c] = sigmoid_f(s);
     }
+}
+
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ partial, int tiles, float inv_hw,
+                                                      const float* __restrict__ w1t,  // [Cse][C]
+                                                      const float* __restrict__ b1,   // [Cse]
+                                                      const float* __restrict__ w2,   // [Cse][C]
+                                                      const float* __restrict__ b2,   // [C]
+                                                      float* __restrict__ gate,       // [N][C]
+                                                      int C, int Cse) {
+    extern __shared__ float sm[];   // mean[C] | hid[Cse]
+    const int n = blockIdx.x;
+    se_gate_crop(partial + (long long)n * tiles * C, tiles, inv_hw, w1t, b1, w2, b2, gate + (long long)n * C, C, Cse, sm);
 }
 
 // ----------------------------------------------------------------------------- head: GAP + 3 Dense + softmax + expectation

@@ -110,6 +110,7 @@ struct whenet_ctx {
     int pw_variant = 2;     // tensor-core 1x1 kernel: 1 = register-staged 2-stage ring, 2 = cp.async ring + in-smem SE gate
     int stem_variant = 1;   // 0 = 4 threads / pixel straight from global, 1 = smem-tiled, weights in the constant bank
     whenet::StemParams stem_params{};
+    int host_chunk = 256;   // host inputs run in passes of at most this many crops so the H2D of pass i+1 hides behind pass i
     int use_graph = 0;      // replay device-resident forwards from a captured CUDA graph (small-batch latency)
     std::vector<GraphEntry> graphs;
     int use_fused = 0;      // K1: expand + depthwise in one kernel (16-bit storage only; default on for bf16/fp16)
@@ -128,6 +129,8 @@ struct whenet_ctx {
     int ws_chunk = 0;
     void *bufA = nullptr, *bufB = nullptr, *bufE = nullptr, *bufD = nullptr;
     float *d_partial = nullptr, *d_gate = nullptr, *d_angles = nullptr, *d_logits = nullptr, *d_pooled = nullptr;
+    int* d_se_counter = nullptr;   // per-crop tickets of the fused SE excite (zero between kernels)
+    int se_fused = 1;              // K1's last CTA per crop computes the SE gate (no se_gate launch)
     void* d_in[2] = {nullptr, nullptr};
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     // crop front-end staging
@@ -228,6 +231,8 @@ void free_ws(whenet_ctx* c) {
         if (*p) cudaFree(*p);
         *p = nullptr;
     }
+    if (c->d_se_counter) cudaFree(c->d_se_counter);
+    c->d_se_counter = nullptr;
     c->ws_chunk = 0;
 }
 
@@ -253,6 +258,8 @@ int ensure_ws(whenet_ctx* c) {
     CK(cudaMalloc(&c->d_partial, ch * part * sizeof(float)));         // [crop][<= ceil(hout/8) tiles][cexp]
     CK(cudaMalloc(&c->d_gate, ch * 1152 * sizeof(float)));
     CK(cudaMalloc(&c->d_pooled, ch * 1280 * sizeof(float)));
+    CK(cudaMalloc(&c->d_se_counter, ch * sizeof(int)));
+    CK(cudaMemset(c->d_se_counter, 0, ch * sizeof(int)));
     for (int i = 0; i < 2; ++i) CK(cudaMalloc(&c->d_in[i], ch * kImgElems * sizeof(float)));
     c->ws_chunk = c->chunk;
     return 0;
@@ -349,6 +356,8 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
             if (c->use_fused && c->k1[i].valid && b.idx <= c->fused_max_block) {
                 whenet::fused::K1Params p = c->k1[i].p;
                 p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial;
+                p.w_se1t = w.w_se1t; p.b_se1 = w.b_se1; p.w_se2 = w.w_se2; p.b_se2 = w.b_se2; p.gate = c->d_gate; p.Cse = b.cse;
+                p.se_counter = c->se_fused ? c->d_se_counter : nullptr;
                 snprintf(nm, sizeof nm, "b%02d.k1", b.idx);
                 Scope sc(c, nm, (double)nb * ((double)b.hin * b.hin * b.cin + (double)b.hout * b.hout * b.cexp) * sizeof(T),
                          2.0 * nb * ((double)b.hin * b.hin * b.cin * b.cexp + (double)b.hout * b.hout * b.k * b.k * b.cexp));
@@ -373,7 +382,7 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
         if (rc) return rc;
         }
         int rc = 0;
-        {
+        if (!(did_k1 && c->se_fused)) {
             snprintf(nm, sizeof nm, "b%02d.se", b.idx);
             Scope sc(c, nm, (double)nb * (tiles + 1) * b.cexp * 4.0, 4.0 * nb * b.cexp * b.cse);
             whenet::se_gate_kernel<<<nb, 256, (b.cexp + b.cse) * sizeof(float), c->stream>>>(
@@ -414,7 +423,7 @@ void drop_graphs(whenet_ctx* c) {
 }
 
 int options_signature(const whenet_ctx* c) {
-    return c->chunk * 1000003 + c->use_tc * 64 + c->dw_variant * 32 + c->use_fused * 16 + c->stem_variant * 8 + c->pw_variant * 2 + c->fused_max_block * 128;
+    return c->chunk * 1000003 + c->se_fused * 4096 + c->use_tc * 64 + c->dw_variant * 32 + c->use_fused * 16 + c->stem_variant * 8 + c->pw_variant * 2 + c->fused_max_block * 128;
 }
 
 template <typename T, bool IN_U8>
@@ -438,9 +447,10 @@ int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* a
         CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     }
     const int64_t launches0 = c->launches;
+    const int step = in_is_device ? c->chunk : std::max(1, std::min(c->chunk, c->host_chunk));
     int ci = 0;
-    for (int off = 0; off < n; off += c->chunk, ++ci) {
-        const int nb = std::min(c->chunk, n - off);
+    for (int off = 0; off < n; off += step, ++ci) {
+        const int nb = std::min(step, n - off);
         const void* d_in;
         const int slot = ci & 1;
         if (in_is_device) {
@@ -994,6 +1004,8 @@ int64_t whenet_launch_count(whenet_ctx* c) { return c ? c->launches : 0; }
 int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!c || !key) return fail(WHENET_EINVAL, "bad arguments");
     if (!strcmp(key, "tensor_cores")) { c->use_tc = value && c->precision != WHENET_PRECISION_FP32; return 0; }
+    if (!strcmp(key, "se_fused")) { c->se_fused = value; return 0; }
+    if (!strcmp(key, "host_chunk")) { if (value < 1) return fail(WHENET_EINVAL, "host_chunk must be >= 1"); c->host_chunk = value; return 0; }
     if (!strcmp(key, "graph")) { c->use_graph = value; if (!value) drop_graphs(c); return 0; }
     if (!strcmp(key, "dw_variant")) { c->dw_variant = value; return 0; }
     if (!strcmp(key, "stem_variant")) { c->stem_variant = value; return 0; }
