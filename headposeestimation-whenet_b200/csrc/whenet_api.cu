@@ -20,6 +20,7 @@
 #include "kernels_tc.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_crop.cuh"
+#include "kernels_k0.cuh"
 
 namespace {
 
@@ -110,7 +111,10 @@ struct whenet_ctx {
     int pw_variant = 2;     // tensor-core 1x1 kernel: 1 = register-staged 2-stage ring, 2 = cp.async ring + in-smem SE gate
     int stem_variant = 1;   // 0 = 4 threads / pixel straight from global, 1 = smem-tiled, weights in the constant bank
     whenet::StemParams stem_params{};
-    int host_chunk = 256;   // host inputs run in passes of at most this many crops so the H2D of pass i+1 hides behind pass i
+    whenet::StemParams stem_params_h{};   // 0.5 * (weights, shift) for K0
+    int use_k0 = 0;                       // stem + block-1 depthwise fused (16-bit modes, uint8 input)
+    int host_chunk = 1 << 30;   // host inputs can run in passes of at most this many crops so the H2D of pass i+1 hides behind
+                                // pass i; measured on B200 (round 1): whole-batch passes win (45.3k vs 42.1k crops/s at 256)
     int use_graph = 0;      // replay device-resident forwards from a captured CUDA graph (small-batch latency)
     std::vector<GraphEntry> graphs;
     int use_fused = 0;      // K1: expand + depthwise in one kernel (16-bit storage only; default on for bf16/fp16)
@@ -130,7 +134,9 @@ struct whenet_ctx {
     void *bufA = nullptr, *bufB = nullptr, *bufE = nullptr, *bufD = nullptr;
     float *d_partial = nullptr, *d_gate = nullptr, *d_angles = nullptr, *d_logits = nullptr, *d_pooled = nullptr;
     int* d_se_counter = nullptr;   // per-crop tickets of the fused SE excite (zero between kernels)
-    int se_fused = 1;              // K1's last CTA per crop computes the SE gate (no se_gate launch)
+    int se_fused = 0;              // K1's/K0's last CTA per crop computes the SE gate (no se_gate launch).  Measured on
+                                   // B200 (round 1): the fence + ticket tail costs more (+0.7 ms / 512 crops) than the 15
+                                   // small se_gate launches it saves (0.37 ms), so it is off by default.
     void* d_in[2] = {nullptr, nullptr};
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     // crop front-end staging
@@ -334,7 +340,22 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
     T* oth = (T*)c->bufB;
     T* E = (T*)c->bufE;
     T* D = (T*)c->bufD;
-    {
+    bool did_k0 = false;
+    if constexpr (sizeof(T) == 2 && IN_U8) {
+        if (c->use_k0 && !taps) {
+            const BlockW& w1 = c->bw[0];
+            whenet::fused::K0Params p{};
+            p.in = (const uint8_t*)d_in; p.lut = c->lut; p.w_dw = w1.w_dw_h; p.b_dw = w1.b_dw_h; p.out = D; p.partial = c->d_partial;
+            p.w_se1t = w1.w_se1t; p.b_se1 = w1.b_se1; p.w_se2 = w1.w_se2; p.b_se2 = w1.b_se2; p.gate = c->d_gate;
+            p.se_counter = c->se_fused ? c->d_se_counter : nullptr; p.Cse = c->blocks[0].cse;
+            Scope sc(c, "k0.stem_dw1", (double)nb * (kImgElems + 112.0 * 112 * 32 * sizeof(T)),
+                     2.0 * nb * (112.0 * 112 * 27 * 32 + 112.0 * 112 * 9 * 32));
+            whenet::fused::k0_stem_dw_kernel<T><<<dim3(64, nb), 256, 0, c->stream>>>(c->stem_params_h, p);
+            CK(cudaGetLastError());
+            did_k0 = true;
+        }
+    }
+    if (!did_k0) {
         Scope sc(c, "stem", (double)nb * (kImgElems * (IN_U8 ? 1.0 : 4.0) + 112.0 * 112 * 32 * sizeof(T)),
                  2.0 * nb * 112.0 * 112 * 27 * 32);
         if (c->stem_variant == 0) {
@@ -352,6 +373,7 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
         const T* dw_in = cur;
         int tiles = 0;
         bool did_k1 = false;
+        if (i == 0 && did_k0) { did_k1 = true; tiles = 64; }      // K0 already produced D, the partials and the gate
         if constexpr (sizeof(T) == 2) {
             if (c->use_fused && c->k1[i].valid && b.idx <= c->fused_max_block) {
                 whenet::fused::K1Params p = c->k1[i].p;
@@ -423,7 +445,7 @@ void drop_graphs(whenet_ctx* c) {
 }
 
 int options_signature(const whenet_ctx* c) {
-    return c->chunk * 1000003 + c->se_fused * 4096 + c->use_tc * 64 + c->dw_variant * 32 + c->use_fused * 16 + c->stem_variant * 8 + c->pw_variant * 2 + c->fused_max_block * 128;
+    return c->chunk * 1000003 + c->use_k0 * 8192 + c->se_fused * 4096 + c->use_tc * 64 + c->dw_variant * 32 + c->use_fused * 16 + c->stem_variant * 8 + c->pw_variant * 2 + c->fused_max_block * 128;
 }
 
 template <typename T, bool IN_U8>
@@ -672,6 +694,8 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
         o_wstem = put(w); o_bstem = put(b); o_lut = put(lut);
         memcpy(c->stem_params.w, w.data(), sizeof(c->stem_params.w));
         memcpy(c->stem_params.b, b.data(), sizeof(c->stem_params.b));
+        for (int i = 0; i < 27 * 32; ++i) c->stem_params_h.w[i] = 0.5f * w[i];
+        for (int i = 0; i < 32; ++i) c->stem_params_h.b[i] = 0.5f * b[i];
     }
     // ---- 16 MBConv blocks
     for (size_t i = 0; i < c->blocks.size(); ++i) {
@@ -1005,6 +1029,7 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!c || !key) return fail(WHENET_EINVAL, "bad arguments");
     if (!strcmp(key, "tensor_cores")) { c->use_tc = value && c->precision != WHENET_PRECISION_FP32; return 0; }
     if (!strcmp(key, "se_fused")) { c->se_fused = value; return 0; }
+    if (!strcmp(key, "k0")) { c->use_k0 = value && c->precision != WHENET_PRECISION_FP32; return 0; }
     if (!strcmp(key, "host_chunk")) { if (value < 1) return fail(WHENET_EINVAL, "host_chunk must be >= 1"); c->host_chunk = value; return 0; }
     if (!strcmp(key, "graph")) { c->use_graph = value; if (!value) drop_graphs(c); return 0; }
     if (!strcmp(key, "dw_variant")) { c->dw_variant = value; return 0; }

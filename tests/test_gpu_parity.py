@@ -270,6 +270,26 @@ def test_empty_batch(net32):
     assert y.shape == (0,) and y.dtype == np.float32
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_k0_stem_dw1_fusion(prec, sample_crops, jitter_crops, golden):
+    """K0 (stem + block-1 depthwise + SE in one kernel, stem output kept in shared memory) against the unfused path
+    and the oracle; and it must stay batch invariant."""
+    import whenet_b200
+    crops = np.concatenate([sample_crops, jitter_crops])
+    ref = np.array([[s["yaw"], s["pitch"], s["roll"]] for s in golden["samples"]] +
+                   list(zip(golden["jitter"]["yaw"], golden["jitter"]["pitch"], golden["jitter"]["roll"])))
+    m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=16)
+    base = np.stack(m.get_angle(crops), axis=1)
+    m.set_option("k0", 1)
+    got = np.stack(m.get_angle(crops), axis=1)
+    tol = 1.5 if prec == "bf16" else 0.15
+    assert np.abs(got - ref).max() <= tol
+    assert np.abs(got - base).max() <= (0.6 if prec == "bf16" else 0.08)
+    one = np.stack(m.get_angle(crops[5:6]), axis=1)
+    assert np.array_equal(one[0], got[5])
+    m.close()
+
+
 def test_cuda_graph_replay(sample_crops, jitter_crops):
     """Device-resident forwards replayed from a captured CUDA graph give bit-identical results, also after the
     input buffer CONTENT changes (same addresses), and new shapes capture new graphs."""
