@@ -215,32 +215,37 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = s_tmem_base;
 
+    // tensor-core work runs one chunk AHEAD of the CUDA-core work: MMA(ch+1) is issued as soon as epilogue 1 has
+    // drained TMEM(ch) and executes while the whole CTA is busy with the depthwise of chunk ch.
+    auto issue_mma = [&](int buf) {
+        const int ksteps_total = p.cpr >> 1;
+        for (int mt = 0; mt < p.mtiles; ++mt) {
+            for (int ks = 0; ks < ksteps_total; ++ks) {
+                const int kb = ks >> 2, k = ks & 3;
+                const uint64_t ad = tc::make_desc(sA + (uint32_t)kb * rows_total * 128 + (uint32_t)mt * BM * 128);
+                const uint64_t bd = tc::make_desc(sW + buf * p.smem_W + (uint32_t)kb * p.CC * 128);
+                tc::umma_f16(tmem_d + (uint32_t)(mt * p.CC), ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), p.idesc, ks ? 1u : 0u);
+            }
+        }
+        tc::umma_commit(&mbar);
+    };
+    // chunk 0: operands (A, W0, constants 0) have to land first
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        issue_mma(0);
+    }
+
     for (int ch = 0; ch < p.n_chunks; ++ch) {
         const int buf = ch & 1;
         const int cbase = ch * p.CC;
-        // operands of this chunk (and, the first time, A) have landed; make them visible to the tensor core
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int ksteps_total = p.cpr >> 1;
-            for (int mt = 0; mt < p.mtiles; ++mt) {
-                for (int ks = 0; ks < ksteps_total; ++ks) {
-                    const int kb = ks >> 2, k = ks & 3;
-                    const uint64_t ad = tc::make_desc(sA + (uint32_t)kb * rows_total * 128 + (uint32_t)mt * BM * 128);
-                    const uint64_t bd = tc::make_desc(sW + buf * p.smem_W + (uint32_t)kb * p.CC * 128);
-                    tc::umma_f16(tmem_d + (uint32_t)(mt * p.CC), ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), p.idesc, ks ? 1u : 0u);
-                }
-            }
-            tc::umma_commit(&mbar);
-        }
-        // next chunk's W + constants stream in behind the MMAs / epilogue / depthwise of this one
+        // next chunk's W + constants stream in behind the epilogue / depthwise of this one
         if (ch + 1 < p.n_chunks) prefetch_chunk(ch + 1, buf ^ 1);
-        if (!tc::mbar_wait(&mbar, ch & 1)) s_abort = 1;
+        if (!tc::mbar_wait(&mbar, ch & 1)) s_abort = 1;          // MMA(ch): issued one phase ago, normally long done
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        __syncthreads();
         const bool ok = !s_abort;
 
         // ---- epilogue 1: TMEM -> swish -> E (16-bit).  The BN shift is already in the accumulator.
@@ -271,8 +276,15 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
                 }
             }
         }
+        // TMEM(ch) is drained and E(ch) is complete; W(ch+1) has landed -> hand the tensor core its next chunk
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
+        if (tid == 0 && ch + 1 < p.n_chunks && !s_abort) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            issue_mma(buf ^ 1);
+        }
 
         // ---- depthwise on E: 8-byte ld.shared, fp32 FMA, weights of one kernel row from smem
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
