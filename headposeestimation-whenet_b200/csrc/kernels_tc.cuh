@@ -436,6 +436,24 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
         const uint32_t a_st = smem0 + s * stage_bytes, w_st = a_st + A_STAGE_BYTES;
         const int kc0 = kb * 8;
         const int cb = min(8, kchunks - kc0), cbp = (cb + 1) & ~1;
+        if (cbp == 8) {
+            // full block: item idx = tid + i*128 -> row tid/8 + 16 i, chunk tid%8 (no divisions in the hot loop)
+            const int c = tid & 7, r0 = tid >> 3;
+            const bool cvalid = c < cb;
+            const T* asrc = A + (long long)(m0 + r0) * K + (kc0 + c) * 8;
+            const uint32_t swz = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((c ^ (r0 & 7)) << 4));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool valid = cvalid && (r0 + 16 * i) < rows_valid;
+                cp_async16_z(a_st + swz + i * 2048, valid ? asrc + (long long)i * 16 * K : A, valid);
+            }
+            const T* wsrc = Wt + (long long)(n0 + r0) * K + (kc0 + c) * 8;
+            for (int r = r0, i = 0; r < umma_n; r += 16, ++i) {
+                const bool valid = cvalid && r < n_valid;
+                cp_async16_z(w_st + swz + i * 2048, valid ? wsrc + (long long)i * 16 * K : Wt, valid);
+            }
+            return;
+        }
         for (int idx = tid; idx < BM * cbp; idx += 128) {
             const int r = idx / cbp, c = idx - r * cbp;
             const bool valid = r < rows_valid && c < cb;
@@ -470,20 +488,44 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
             const int kc0 = kb * 8;
             const int cb = min(8, kchunks - kc0), cbp = (cb + 1) & ~1;
             if (GATE == 1) {
-                for (int idx = tid; idx < BM * cbp; idx += 128) {
-                    const int r = idx / cbp, c = idx - r * cbp;
-                    if (r < rows_valid && c < cb) {
-                        const uint32_t addr = a_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
-                        const int cr = (m0 + r) / hw - crop0;
-                        sts128_(addr, scale8s<T>(lds128(addr), sG + (uint32_t)(cr * K + (kc0 + c) * 8) * 4));
+                if (cbp == 8) {
+                    const int c = tid & 7, r0 = tid >> 3;
+                    if (c < cb) {
+                        const uint32_t a0 = a_st + (r0 >> 3) * 1024 + (r0 & 7) * 128 + ((c ^ (r0 & 7)) << 4);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = r0 + 16 * i;
+                            if (r < rows_valid) {
+                                const int cr = (m0 + r) / hw - crop0;
+                                sts128_(a0 + i * 2048, scale8s<T>(lds128(a0 + i * 2048), sG + (uint32_t)(cr * K + (kc0 + c) * 8) * 4));
+                            }
+                        }
+                    }
+                } else {
+                    for (int idx = tid; idx < BM * cbp; idx += 128) {
+                        const int r = idx / cbp, c = idx - r * cbp;
+                        if (r < rows_valid && c < cb) {
+                            const uint32_t addr = a_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+                            const int cr = (m0 + r) / hw - crop0;
+                            sts128_(addr, scale8s<T>(lds128(addr), sG + (uint32_t)(cr * K + (kc0 + c) * 8) * 4));
+                        }
                     }
                 }
             } else {
-                for (int idx = tid; idx < umma_n * cbp; idx += 128) {
-                    const int r = idx / cbp, c = idx - r * cbp;
-                    if (r < n_valid && c < cb) {
-                        const uint32_t addr = w_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
-                        sts128_(addr, scale8s<T>(lds128(addr), sG + (uint32_t)((kc0 + c) * 8) * 4));
+                if (cbp == 8) {
+                    const int c = tid & 7, r0 = tid >> 3;
+                    if (c < cb)
+                        for (int r = r0, i = 0; r < n_valid; r += 16, ++i) {
+                            const uint32_t addr = w_st + (r0 >> 3) * 1024 + (r0 & 7) * 128 + ((c ^ (r0 & 7)) << 4) + i * 2048;
+                            sts128_(addr, scale8s<T>(lds128(addr), sG + (uint32_t)((kc0 + c) * 8) * 4));
+                        }
+                } else {
+                    for (int idx = tid; idx < umma_n * cbp; idx += 128) {
+                        const int r = idx / cbp, c = idx - r * cbp;
+                        if (r < n_valid && c < cb) {
+                            const uint32_t addr = w_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+                            sts128_(addr, scale8s<T>(lds128(addr), sG + (uint32_t)((kc0 + c) * 8) * 4));
+                        }
                     }
                 }
             }
@@ -564,7 +606,7 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
 
 template <typename T>
 int launch_pw_tc2(cudaStream_t stream, const T* A, const void* Wt16, const float* bias, const float* gate, const T* resid,
-                  T* out, long long M, int K, int N, int hw, bool swish) {
+                  T* out, long long M, int K, int N, int hw, bool swish, int stage_cap = 0, int smem_budget_kb = 108) {
     if (sizeof(T) != 2) return 1;
     if ((K & 7) || (N & 7) || M > 0x7fffffffLL) return 1;
     const bool per_crop = gate && hw >= 784;                 // gate on W, tiles stay inside a crop
@@ -594,7 +636,9 @@ int launch_pw_tc2(cudaStream_t stream, const T* A, const void* Wt16, const float
     const size_t gate_bytes = gate ? (size_t)(per_crop ? 1 : 4) * K * 4 : 0;
     const size_t out_bytes = (size_t)BM * ((size_t)(n_tile >> 3) | 1) * 16;
     int n_stages = nkb < 4 ? nkb : 4;
-    while (n_stages > 2 && n_stages * stage_bytes + gate_bytes > 108 * 1024) --n_stages;   // keep two CTAs per SM
+    if (stage_cap > 0 && n_stages > stage_cap) n_stages = stage_cap;
+    // ring depth vs co-residency: a shallower ring lets more CTAs share the SM (budget = smem per CTA)
+    while (n_stages > 2 && n_stages * stage_bytes + gate_bytes > (size_t)smem_budget_kb * 1024) --n_stages;
     size_t smem = n_stages * stage_bytes + gate_bytes;
     if (smem < out_bytes) smem = out_bytes;
     smem += 1024;

@@ -108,6 +108,7 @@ struct whenet_ctx {
     int use_tc = 0;         // tensor-core kernels for the 1x1 convs
     bool tc_used = false;   // a tcgen05 kernel ran since the last timeout-flag check
     int dw_variant = 1;     // 0 = one output per thread, 1 = register-blocked strips
+    int pw_stage_cap = 0, pw_smem_kb = 108;   // pw_tc2 ring: max stages (0 = up to 4) and per-CTA smem budget that trades depth for co-residency
     int pw_variant = 2;     // tensor-core 1x1 kernel: 1 = register-staged 2-stage ring, 2 = cp.async ring + in-smem SE gate
     int stem_variant = 1;   // 0 = 4 threads / pixel straight from global, 1 = smem-tiled, weights in the constant bank
     whenet::StemParams stem_params{};
@@ -280,7 +281,7 @@ int launch_pw(whenet_ctx* c, const char* name, const T* A, const float* W, const
     Scope sc(c, name, bytes, flops);
     if constexpr (sizeof(T) == 2) {
         if (c->use_tc && Wt16) {
-            int rc = c->pw_variant == 2 ? whenet::tc::launch_pw_tc2<T>(c->stream, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish)
+            int rc = c->pw_variant == 2 ? whenet::tc::launch_pw_tc2<T>(c->stream, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish, c->pw_stage_cap, c->pw_smem_kb)
                                         : whenet::tc::launch_pw_tc<T>(c->stream, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish);
             if (rc == 0) { CK(cudaGetLastError()); c->tc_used = true; return 0; }
             if (rc < 0) return fail(WHENET_ECUDA, "tensor-core 1x1 launch failed for %s (rc=%d)", name, rc);
@@ -1035,6 +1036,8 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!strcmp(key, "dw_variant")) { c->dw_variant = value; return 0; }
     if (!strcmp(key, "stem_variant")) { c->stem_variant = value; return 0; }
     if (!strcmp(key, "pw_variant")) { c->pw_variant = value; return 0; }
+    if (!strcmp(key, "pw_stage_cap")) { c->pw_stage_cap = value; return 0; }
+    if (!strcmp(key, "pw_smem_kb")) { c->pw_smem_kb = value; return 0; }
     if (!strcmp(key, "fused")) { c->use_fused = value && c->precision != WHENET_PRECISION_FP32; return 0; }
     if (!strcmp(key, "fused_max_block")) { c->fused_max_block = value; return 0; }
     if (!strcmp(key, "chunk")) {
