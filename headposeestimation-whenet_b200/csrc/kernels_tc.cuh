@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
 
 template <typename T>
 int launch_pw_tc2(cudaStream_t stream, const T* A, const void* Wt16, const float* bias, const float* gate, const T* resid,
-                  T* out, long long M, int K, int N, int hw, bool swish, int stage_cap = 0, int smem_budget_kb = 108) {
+                  T* out, long long M, int K, int N, int hw, bool swish, int stage_cap = 0, int smem_budget_kb = 54) {
     if (sizeof(T) != 2) return 1;
     if ((K & 7) || (N & 7) || M > 0x7fffffffLL) return 1;
     const bool per_crop = gate && hw >= 784;                 // gate on W, tiles stay inside a crop

@@ -108,7 +108,7 @@ struct whenet_ctx {
     int use_tc = 0;         // tensor-core kernels for the 1x1 convs
     bool tc_used = false;   // a tcgen05 kernel ran since the last timeout-flag check
     int dw_variant = 1;     // 0 = one output per thread, 1 = register-blocked strips
-    int pw_stage_cap = 0, pw_smem_kb = 108;   // pw_tc2 ring: max stages (0 = up to 4) and per-CTA smem budget that trades depth for co-residency
+    int pw_stage_cap = 0, pw_smem_kb = 54;    // pw_tc2 ring: max stages (0 = up to 4) and per-CTA smem budget that trades depth for co-residency
     int pw_variant = 2;     // tensor-core 1x1 kernel: 1 = register-staged 2-stage ring, 2 = cp.async ring + in-smem SE gate
     int stem_variant = 1;   // 0 = 4 threads / pixel straight from global, 1 = smem-tiled, weights in the constant bank
     whenet::StemParams stem_params{};
