@@ -19,6 +19,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_fused.cuh"
+#include "kernels_fused_tc.cuh"
 #include "kernels_crop.cuh"
 #include "kernels_k0.cuh"
 
@@ -90,6 +91,7 @@ struct BlockW {   // device pointers into the fp32 arena
 };
 
 struct K1Plan { bool valid = false; whenet::fused::K1Params p{}; int R = 0; size_t smem = 0; };
+struct K1TPlan { bool valid = false; whenet::fused::K1TParams p{}; size_t smem = 0; };
 struct GraphKey {
     int n, in_u8, sig;
     const void* in;
@@ -121,6 +123,9 @@ struct whenet_ctx {
     int use_fused = 0;      // K1: expand + depthwise in one kernel (16-bit storage only; default on for bf16/fp16)
     int fused_max_block = 16;  // blocks 2..fused_max_block use K1
     std::vector<K1Plan> k1;
+    std::vector<K1TPlan> k1t;
+    int k1_variant = 1;        // 1 = K1 (depthwise on CUDA cores), 2 = K1T (depthwise on the tensor core via diagonal weights)
+    int k1t_max_block = 16;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     bool weights_loaded = false;
     std::vector<BlockCfg> blocks;
@@ -258,6 +263,8 @@ int ensure_ws(whenet_ctx* c) {
     }
     for (const K1Plan& pl : c->k1)
         if (pl.valid) part = std::max(part, (size_t)pl.p.tiles_x * pl.p.tiles_y * pl.p.Cexp);
+    for (const K1TPlan& pl : c->k1t)
+        if (pl.valid) part = std::max(part, (size_t)pl.p.tiles_x * pl.p.tiles_y * pl.p.Cexp);
     CK(cudaMalloc(&c->bufA, ch * io * es));
     CK(cudaMalloc(&c->bufB, ch * io * es));
     CK(cudaMalloc(&c->bufE, ch * ex * es));
@@ -376,7 +383,19 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
         bool did_k1 = false;
         if (i == 0 && did_k0) { did_k1 = true; tiles = 64; }      // K0 already produced D, the partials and the gate
         if constexpr (sizeof(T) == 2) {
-            if (c->use_fused && c->k1[i].valid && b.idx <= c->fused_max_block) {
+            if (c->use_fused && c->k1_variant == 2 && c->k1t[i].valid && b.idx <= c->k1t_max_block) {
+                whenet::fused::K1TParams p = c->k1t[i].p;
+                p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial;
+                snprintf(nm, sizeof nm, "b%02d.k1", b.idx);
+                Scope sc(c, nm, (double)nb * ((double)b.hin * b.hin * b.cin + (double)b.hout * b.hout * b.cexp) * sizeof(T),
+                         2.0 * nb * ((double)b.hin * b.hin * b.cin * b.cexp + (double)b.hout * b.hout * b.k * b.k * b.cexp));
+                int rc = whenet::fused::launch_k1t<T>(c->stream, p, b.k, b.s, c->k1t[i].smem, nb);
+                if (rc != 0) return fail(WHENET_ECUDA, "K1T launch failed for block %d (rc=%d)", b.idx, rc);
+                CK(cudaGetLastError());
+                c->tc_used = true;
+                tiles = p.tiles_x * p.tiles_y;
+                did_k1 = true;
+            } else if (c->use_fused && c->k1[i].valid && b.idx <= c->fused_max_block) {
                 whenet::fused::K1Params p = c->k1[i].p;
                 p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial;
                 p.w_se1t = w.w_se1t; p.b_se1 = w.b_se1; p.w_se2 = w.w_se2; p.b_se2 = w.b_se2; p.gate = c->d_gate; p.Cse = b.cse;
@@ -405,7 +424,7 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
         if (rc) return rc;
         }
         int rc = 0;
-        if (!(did_k1 && c->se_fused)) {
+        if (!(did_k1 && c->se_fused && c->k1_variant == 1)) {
             snprintf(nm, sizeof nm, "b%02d.se", b.idx);
             Scope sc(c, nm, (double)nb * (tiles + 1) * b.cexp * 4.0, 4.0 * nb * b.cexp * b.cse);
             whenet::se_gate_kernel<<<nb, 256, (b.cexp + b.cse) * sizeof(float), c->stream>>>(
@@ -446,7 +465,7 @@ void drop_graphs(whenet_ctx* c) {
 }
 
 int options_signature(const whenet_ctx* c) {
-    return c->chunk * 1000003 + c->use_k0 * 8192 + c->se_fused * 4096 + c->use_tc * 64 + c->dw_variant * 32 + c->use_fused * 16 + c->stem_variant * 8 + c->pw_variant * 2 + c->fused_max_block * 128;
+    return c->chunk * 1000003 + c->k1_variant * 16384 + c->k1t_max_block * 65536 + c->use_k0 * 8192 + c->se_fused * 4096 + c->use_tc * 64 + c->dw_variant * 32 + c->use_fused * 16 + c->stem_variant * 8 + c->pw_variant * 2 + c->fused_max_block * 128;
 }
 
 template <typename T, bool IN_U8>
@@ -613,6 +632,7 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
     c->blocks = make_blocks();
     c->bw.resize(c->blocks.size());
     c->k1.resize(c->blocks.size());
+    c->k1t.resize(c->blocks.size());
     if (precision != WHENET_PRECISION_FP32)
         for (size_t i = 0; i < c->blocks.size(); ++i) {
             const BlockCfg& b = c->blocks[i];
@@ -620,6 +640,9 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
             K1Plan& pl = c->k1[i];
             pl.valid = whenet::fused::plan_k1(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, precision == WHENET_PRECISION_BF16,
                                               &pl.p, &pl.R, &pl.smem);
+            K1TPlan& pt = c->k1t[i];
+            pt.valid = whenet::fused::plan_k1t(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, precision == WHENET_PRECISION_BF16,
+                                               &pt.p, &pt.smem);
         }
     c->use_fused = precision != WHENET_PRECISION_FP32;
     if (const char* e3 = getenv("WHENET_FUSED")) c->use_fused = atoi(e3) && precision != WHENET_PRECISION_FP32;
@@ -1036,6 +1059,8 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!strcmp(key, "dw_variant")) { c->dw_variant = value; return 0; }
     if (!strcmp(key, "stem_variant")) { c->stem_variant = value; return 0; }
     if (!strcmp(key, "pw_variant")) { c->pw_variant = value; return 0; }
+    if (!strcmp(key, "k1_variant")) { c->k1_variant = value; return 0; }
+    if (!strcmp(key, "k1t_max_block")) { c->k1t_max_block = value; return 0; }
     if (!strcmp(key, "pw_stage_cap")) { c->pw_stage_cap = value; return 0; }
     if (!strcmp(key, "pw_smem_kb")) { c->pw_smem_kb = value; return 0; }
     if (!strcmp(key, "fused")) { c->use_fused = value && c->precision != WHENET_PRECISION_FP32; return 0; }

@@ -150,6 +150,33 @@ def test_fused_k1_taps(prec, oracle32, sample_crops):
     m.close()
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_fused_k1t_tensor_core_depthwise(prec, oracle32, sample_crops):
+    """K1T: the depthwise runs on the tensor core too (shifted views of the expanded tile x diagonal weight matrices);
+    every depthwise output, SE gate and block output against the oracle."""
+    import whenet_b200
+    m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=8)
+    m.set_option("fused", 1)
+    m.set_option("k1_variant", 2)
+    taps = {}
+    oracle32.get_angle(sample_crops, taps)
+    m.enable_taps(True)
+    got = np.stack(m.get_angle(sample_crops), axis=1)
+    lim = 0.12 if prec == "bf16" else 0.02
+    for i in range(1, 17):
+        for kind in ("dw", "gate", "block"):
+            nm = "%s%d" % (kind, i)
+            ref = taps[nm].astype(np.float64).reshape(-1)
+            g = m.tap(nm).astype(np.float64)
+            e = float(np.sqrt(((g - ref) ** 2).mean()) / (np.sqrt((ref ** 2).mean()) + 1e-30))
+            assert e < lim, (nm, e)
+    ref_ang = np.stack(oracle32.get_angle(sample_crops), axis=1)
+    assert np.abs(got - ref_ang).max() < (1.5 if prec == "bf16" else 0.15)
+    one = np.stack(m.get_angle(sample_crops[1:2]), axis=1)
+    assert np.array_equal(one[0], got[1])
+    m.close()
+
+
 def test_fused_k1_batch_invariance(sample_crops, jitter_crops):
     import whenet_b200
     crops = np.concatenate([sample_crops, jitter_crops] * 3)[:19]
