@@ -99,7 +99,9 @@ __device__ __forceinline__ uint32_t sw128(int r, int c) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
-template <typename T, int KS, int S, int R>
+// NOEXP: the block has no expand conv (block 1): the halo tile of the block INPUT is copied straight into E and only the
+// depthwise half of the kernel runs (single chunk, no tensor-core work).
+template <typename T, int KS, int S, int R, bool NOEXP = false>
 __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
@@ -133,13 +135,25 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
         s_abort = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (!NOEXP && warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&s_tmem_base)), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (NOEXP) {
+        // ---- E <- the input halo tile itself (Cin == Cexp == CC), zero outside the image (depthwise SAME padding)
+        const T* in_n = in + (long long)n * p.Hin * p.Hin * p.Cin;
+        const int cpp = p.CC >> 3;                                  // 16-byte chunks per pixel
+        for (int idx = tid; idx < npix * cpp; idx += 256) {
+            const int r = idx / cpp, c = idx - r * cpp;
+            const int ty = r / p.IW, tx = r - ty * p.IW;
+            const int iy = iy0 + ty, ix = ix0 + tx;
+            const bool valid = iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Hin;
+            cp_async16(sE + (uint32_t)r * p.pitchE + c * 16, valid ? in_n + ((long long)iy * p.Hin + ix) * p.Cin + c * 8 : in_n, valid);
+        }
+    }
 
     // ---- A: the input halo tile (cp.async, zero-filled outside the image), + the ones chunk, + an even-count pad chunk
-    {
+    if (!NOEXP) {
         const T* in_n = in + (long long)n * p.Hin * p.Hin * p.Cin;
         // one (pixel, chunk) item per step; walk pixels with a running (ty, tx) instead of dividing
         const int items = npix * kchunks;
@@ -169,7 +183,7 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
         const int cbase = ch * p.CC;
         const uint32_t w_dst = sW + buf * p.smem_W;
         const int per_row = p.cpr;                                 // data chunks + shift chunk (+ zero pad chunk)
-        for (int idx = tid; idx < p.CC * per_row; idx += 256) {
+        for (int idx = tid; idx < (NOEXP ? 0 : p.CC * per_row); idx += 256) {
             const int r = idx / per_row, c = idx - r * per_row;
             const bool valid = c <= kchunks;
             cp_async16(w_dst + (uint32_t)(c >> 3) * p.CC * 128 + sw128(r, c & 7),
@@ -213,7 +227,7 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = s_tmem_base;
+    const uint32_t tmem_d = NOEXP ? 0u : s_tmem_base;
 
     // tensor-core work runs one chunk AHEAD of the CUDA-core work: MMA(ch+1) is issued as soon as epilogue 1 has
     // drained TMEM(ch) and executes while the whole CTA is busy with the depthwise of chunk ch.
@@ -234,7 +248,7 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (tid == 0) {
+    if (!NOEXP && tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         issue_mma(0);
     }
@@ -244,13 +258,15 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
         const int cbase = ch * p.CC;
         // next chunk's W + constants stream in behind the epilogue / depthwise of this one
         if (ch + 1 < p.n_chunks) prefetch_chunk(ch + 1, buf ^ 1);
-        if (!tc::mbar_wait(&mbar, ch & 1)) s_abort = 1;          // MMA(ch): issued one phase ago, normally long done
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (!NOEXP) {
+            if (!tc::mbar_wait(&mbar, ch & 1)) s_abort = 1;      // MMA(ch): issued one phase ago, normally long done
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
         const bool ok = !s_abort;
 
         // ---- epilogue 1: TMEM -> swish -> E (16-bit).  The BN shift is already in the accumulator.
         //      (M tile, 16-column unit) pairs alternate between the two warp halves so both carry the same load.
-        if (ok) {
+        if (ok && !NOEXP) {
             const int half = warp >> 2;
 #pragma unroll
             for (int mt = 0; mt < 3; ++mt) {
@@ -281,7 +297,7 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (tid == 0 && ch + 1 < p.n_chunks && !s_abort) {
+        if (!NOEXP && tid == 0 && ch + 1 < p.n_chunks && !s_abort) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             issue_mma(buf ^ 1);
         }
@@ -358,7 +374,7 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __threadfence();                       // this CTA's squeeze partials are visible device-wide before the ticket
     __syncthreads();
-    if (warp == 0)
+    if (!NOEXP && warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)p.tmem_cols) : "memory");
 
     // ---- SE excite by the last CTA of this crop (classic fence + ticket pattern; the sums stay in fixed order)
@@ -372,7 +388,7 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
         if (s_last && !s_abort) {
             __threadfence();
             float* sm = reinterpret_cast<float*>(smem_raw + (sE - tc::smem_u32(smem_raw)));    // E is free now
-            se_gate_crop(p.partial + (long long)n * gridDim.x * p.Cexp, (int)gridDim.x, 1.0f / (float)(p.Ho * p.Ho),
+            se_gate_crop<true>(p.partial + (long long)n * gridDim.x * p.Cexp, (int)gridDim.x, 1.0f / (float)(p.Ho * p.Ho),
                          p.w_se1t, p.b_se1, p.w_se2, p.b_se2, p.gate + (long long)n * p.Cexp, p.Cexp, p.Cse, sm);
         }
     }
@@ -450,6 +466,33 @@ inline bool plan_k1(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, b
             if (best < 0 || cost < best) { best = cost; *p = q; *R_out = R; *smem_out = smem; found = true; }
         }
     return found;
+}
+
+// Block 1 (no expand conv): 14x14 output tiles, 3x3 stride 1, all 32 channels in one chunk.
+inline bool plan_dw_only(int Hin, int C, int k, int s, int pad, K1Params* p, size_t* smem_out) {
+    if (k != 3 || s != 1 || Hin % 14 || C % 16 || C > 128) return false;
+    *p = K1Params{};
+    p->Hin = Hin; p->Ho = Hin; p->Cin = C; p->Cexp = C; p->pad = pad;
+    p->TH = 14; p->TW = 14; p->IH = 16; p->IW = 16;
+    p->tiles_x = Hin / 14; p->tiles_y = Hin / 14;
+    p->mtiles = 2; p->cpr = 2; p->nkb = 1; p->CC = C; p->n_chunks = 1; p->tmem_cols = 32;
+    p->pitchE = C * 2 + 16;
+    p->PY = 256 / (C / 4);
+    p->spr_log2 = 1;
+    p->smem_A = 0; p->smem_W = 0;
+    p->smem_C = (((k * k + 1) * C * 4) + 1023) & ~1023;
+    p->smem_E = (((16 * 16 + 7 + 16) * p->pitchE) + 1023) & ~1023;
+    *smem_out = (size_t)2 * p->smem_C + p->smem_E + (size_t)p->PY * C * 4 + 1024;
+    return true;
+}
+
+template <typename T>
+int launch_dw_only(cudaStream_t stream, const K1Params& p, size_t smem, int n_crops) {
+    dim3 grid(p.tiles_x * p.tiles_y, n_crops);
+    auto kfn = k1_expand_dw_kernel<T, 3, 1, 7, true>;
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
+    kfn<<<grid, 256, smem, stream>>>(p);
+    return 0;
 }
 
 template <typename T>

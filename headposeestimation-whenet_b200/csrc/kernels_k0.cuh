@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256, 2) k0_stem_dw_kernel(const __grid_constan
         __syncthreads();
         if (s_last) {
             __threadfence();
-            se_gate_crop(p.partial + (long long)n * 64 * 32, 64, 1.0f / (112.0f * 112.0f), p.w_se1t, p.b_se1, p.w_se2, p.b_se2,
+            se_gate_crop<true>(p.partial + (long long)n * 64 * 32, 64, 1.0f / (112.0f * 112.0f), p.w_se1t, p.b_se1, p.w_se2, p.b_se2,
                          p.gate + (long long)n * 32, 32, p.Cse, s_se);
         }
     }

@@ -498,6 +498,7 @@ __global__ void __launch_bounds__(256) dw_strip_kernel(const T* __restrict__ in,
 // Device function for ONE crop, executed by a whole 256-thread CTA: the stand-alone kernel below and the tail of
 // K1 (the last CTA of a crop to finish) both call it.  `sm` = C + Cse floats of shared memory.
 // `partial` is read with ld.global.cg: it may have been written by other CTAs of the same launch.
+template <bool COHERENT>
 __device__ __forceinline__ void se_gate_crop(const float* __restrict__ partial_n, int tiles, float inv_hw,
                                              const float* __restrict__ w1t, const float* __restrict__ b1,
                                              const float* __restrict__ w2, const float* __restrict__ b2,
@@ -506,9 +507,17 @@ __device__ __forceinline__ void se_gate_crop(const float* __restrict__ partial_n
     float* hid = sm + C;
     const int tid = threadIdx.x;
     for (int c = tid; c < C; c += 256) {
-        float s = 0.f;
-        for (int t = 0; t < tiles; ++t) s += __ldcg(partial_n + (long long)t * C + c);
-        mean[c] = s * inv_hw;
+        // four independent partial chains keep several loads in flight; the association order is fixed (t mod 4), so
+        // the sum stays bitwise reproducible
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int t = 0;
+        for (; t + 3 < tiles; t += 4) {
+            const float* q = partial_n + (long long)t * C + c;
+            if (COHERENT) { s0 += __ldcg(q); s1 += __ldcg(q + C); s2 += __ldcg(q + 2 * C); s3 += __ldcg(q + 3 * C); }
+            else { s0 += q[0]; s1 += q[C]; s2 += q[2 * C]; s3 += q[3 * C]; }
+        }
+        for (; t < tiles; ++t) s0 += COHERENT ? __ldcg(partial_n + (long long)t * C + c) : partial_n[(long long)t * C + c];
+        mean[c] = ((s0 + s1) + (s2 + s3)) * inv_hw;
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
@@ -536,7 +545,7 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
                                                       int C, int Cse) {
     extern __shared__ float sm[];   // mean[C] | hid[Cse]
     const int n = blockIdx.x;
-    se_gate_crop(partial + (long long)n * tiles * C, tiles, inv_hw, w1t, b1, w2, b2, gate + (long long)n * C, C, Cse, sm);
+    se_gate_crop<false>(partial + (long long)n * tiles * C, tiles, inv_hw, w1t, b1, w2, b2, gate + (long long)n * C, C, Cse, sm);
 }
 
 // ----------------------------------------------------------------------------- head: GAP + 3 Dense + softmax + expectation

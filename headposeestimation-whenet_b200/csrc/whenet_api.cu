@@ -116,6 +116,10 @@ struct whenet_ctx {
     whenet::StemParams stem_params{};
     whenet::StemParams stem_params_h{};   // 0.5 * (weights, shift) for K0
     int use_k0 = 0;                       // stem + block-1 depthwise fused (16-bit modes, uint8 input)
+    bool async_host = false;    // set by whenet_forward_u8_async for the duration of the call
+    unsigned host_pass_ctr = 0; // staging slot selector, persistent across calls so consecutive calls double-buffer
+    float* d_angles_slot[2] = {nullptr, nullptr};
+    float* d_logits_slot[2] = {nullptr, nullptr};
     int host_chunk = 1 << 30;   // host inputs can run in passes of at most this many crops so the H2D of pass i+1 hides behind
                                 // pass i; measured on B200 (round 1): whole-batch passes win (45.3k vs 42.1k crops/s at 256)
     int use_graph = 0;      // replay device-resident forwards from a captured CUDA graph (small-batch latency)
@@ -124,6 +128,8 @@ struct whenet_ctx {
     int fused_max_block = 16;  // blocks 2..fused_max_block use K1
     std::vector<K1Plan> k1;
     std::vector<K1TPlan> k1t;
+    K1Plan dw1;                // block 1 (no expand): depthwise-only instance of K1
+    int dw1_fused = 1;
     int k1_variant = 1;        // 1 = K1 (depthwise on CUDA cores), 2 = K1T (depthwise on the tensor core via diagonal weights)
     int k1t_max_block = 16;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
@@ -265,6 +271,7 @@ int ensure_ws(whenet_ctx* c) {
         if (pl.valid) part = std::max(part, (size_t)pl.p.tiles_x * pl.p.tiles_y * pl.p.Cexp);
     for (const K1TPlan& pl : c->k1t)
         if (pl.valid) part = std::max(part, (size_t)pl.p.tiles_x * pl.p.tiles_y * pl.p.Cexp);
+    if (c->dw1.valid) part = std::max(part, (size_t)c->dw1.p.tiles_x * c->dw1.p.tiles_y * c->dw1.p.Cexp);
     CK(cudaMalloc(&c->bufA, ch * io * es));
     CK(cudaMalloc(&c->bufB, ch * io * es));
     CK(cudaMalloc(&c->bufE, ch * ex * es));
@@ -383,7 +390,19 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
         bool did_k1 = false;
         if (i == 0 && did_k0) { did_k1 = true; tiles = 64; }      // K0 already produced D, the partials and the gate
         if constexpr (sizeof(T) == 2) {
-            if (c->use_fused && c->k1_variant == 2 && c->k1t[i].valid && b.idx <= c->k1t_max_block) {
+            if (i == 0 && !did_k1 && c->use_fused && c->dw1_fused && c->dw1.valid) {
+                whenet::fused::K1Params p = c->dw1.p;
+                p.in = cur; p.wt_aug = nullptr; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial;
+                p.w_se1t = w.w_se1t; p.b_se1 = w.b_se1; p.w_se2 = w.w_se2; p.b_se2 = w.b_se2; p.gate = c->d_gate; p.Cse = b.cse;
+                p.se_counter = c->se_fused ? c->d_se_counter : nullptr;
+                snprintf(nm, sizeof nm, "b%02d.dw", b.idx);
+                Scope sc(c, nm, (double)nb * 2.0 * b.hin * b.hin * b.cexp * sizeof(T), 2.0 * nb * (double)b.hout * b.hout * b.k * b.k * b.cexp);
+                int rc = whenet::fused::launch_dw_only<T>(c->stream, p, c->dw1.smem, nb);
+                if (rc != 0) return fail(WHENET_ECUDA, "depthwise-only K1 launch failed (rc=%d)", rc);
+                CK(cudaGetLastError());
+                tiles = p.tiles_x * p.tiles_y;
+                did_k1 = true;
+            } else if (c->use_fused && c->k1_variant == 2 && c->k1t[i].valid && b.idx <= c->k1t_max_block) {
                 whenet::fused::K1TParams p = c->k1t[i].p;
                 p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial;
                 snprintf(nm, sizeof nm, "b%02d.k1", b.idx);
@@ -465,7 +484,7 @@ void drop_graphs(whenet_ctx* c) {
 }
 
 int options_signature(const whenet_ctx* c) {
-    return c->chunk * 1000003 + c->k1_variant * 16384 + c->k1t_max_block * 65536 + c->use_k0 * 8192 + c->se_fused * 4096 + c->use_tc * 64 + c->dw_variant * 32 + c->use_fused * 16 + c->stem_variant * 8 + c->pw_variant * 2 + c->fused_max_block * 128;
+    return c->chunk * 1000003 + c->dw1_fused * 3 + c->k1_variant * 16384 + c->k1t_max_block * 65536 + c->use_k0 * 8192 + c->se_fused * 4096 + c->use_tc * 64 + c->dw_variant * 32 + c->use_fused * 16 + c->stem_variant * 8 + c->pw_variant * 2 + c->fused_max_block * 128;
 }
 
 template <typename T, bool IN_U8>
@@ -473,8 +492,9 @@ int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* a
     int rc = ensure_ws(c);
     if (rc) return rc;
     const size_t in_es = IN_U8 ? 1 : 4;
-    float* d_ang = out_is_device ? angles_out : c->d_angles;
-    float* d_log = logits_out ? (out_is_device ? logits_out : c->d_logits) : nullptr;
+    const int oslot = (int)(c->host_pass_ctr & 1u);       // result buffers alternate too: two host calls may be in flight
+    float* d_ang = out_is_device ? angles_out : c->d_angles_slot[oslot];
+    float* d_log = logits_out ? (out_is_device ? logits_out : c->d_logits_slot[oslot]) : nullptr;
     // ---- device-resident forwards can be replayed from a captured graph (66 -> 1 launch; small-batch latency)
     const bool graphable = c->use_graph && in_is_device && out_is_device && !c->prof_on && !c->taps_on;
     GraphKey key{n, IN_U8 ? 1 : 0, options_signature(c), in, d_ang, d_log};
@@ -494,7 +514,7 @@ int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* a
     for (int off = 0; off < n; off += step, ++ci) {
         const int nb = std::min(step, n - off);
         const void* d_in;
-        const int slot = ci & 1;
+        const int slot = in_is_device ? 0 : (int)(c->host_pass_ctr++ & 1u);
         if (in_is_device) {
             d_in = (const char*)in + (size_t)off * kImgElems * in_es;
         } else {
@@ -527,9 +547,11 @@ int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* a
         return 0;
     }
     if (!out_is_device) {
-        CK(cudaMemcpyAsync(angles_out, c->d_angles, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(angles_out, d_ang, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
         if (logits_out)
-            CK(cudaMemcpyAsync(logits_out, c->d_logits, (size_t)n * WHENET_N_LOGITS * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(logits_out, d_log, (size_t)n * WHENET_N_LOGITS * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (in_is_device) c->host_pass_ctr++;            // keep alternating result buffers for device-in / host-out calls too
+        if (c->async_host) return 0;                     // the caller synchronises (whenet_synchronize) before reading
         CK(cudaStreamSynchronize(c->stream));
         if (c->tc_used) {
             c->tc_used = false;
@@ -633,6 +655,11 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
     c->bw.resize(c->blocks.size());
     c->k1.resize(c->blocks.size());
     c->k1t.resize(c->blocks.size());
+    if (precision != WHENET_PRECISION_FP32) {
+        const BlockCfg& b1 = c->blocks[0];
+        c->dw1.valid = !b1.has_expand && whenet::fused::plan_dw_only(b1.hin, b1.cexp, b1.k, b1.s, b1.pad, &c->dw1.p, &c->dw1.smem);
+        c->dw1.R = 7;
+    }
     if (precision != WHENET_PRECISION_FP32)
         for (size_t i = 0; i < c->blocks.size(); ++i) {
             const BlockCfg& b = c->blocks[i];
@@ -653,8 +680,12 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
         CK(cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
     }
-    CK(cudaMalloc(&c->d_angles, (size_t)max_batch * 3 * sizeof(float)));
-    CK(cudaMalloc(&c->d_logits, (size_t)max_batch * WHENET_N_LOGITS * sizeof(float)));
+    CK(cudaMalloc(&c->d_angles, (size_t)max_batch * 3 * sizeof(float) * 2));
+    CK(cudaMalloc(&c->d_logits, (size_t)max_batch * WHENET_N_LOGITS * sizeof(float) * 2));
+    for (int i = 0; i < 2; ++i) {
+        c->d_angles_slot[i] = c->d_angles + (size_t)i * max_batch * 3;
+        c->d_logits_slot[i] = c->d_logits + (size_t)i * max_batch * WHENET_N_LOGITS;
+    }
     *out = c;
     return 0;
 }
@@ -844,6 +875,14 @@ int whenet_set_stream(whenet_ctx* c, void* s) {
 
 int whenet_forward_u8(whenet_ctx* c, const uint8_t* in, int n, int in_is_device, float* angles, float* logits, int out_is_device) {
     return forward_dispatch<true>(c, in, n, in_is_device, angles, logits, out_is_device);
+}
+
+int whenet_forward_u8_async(whenet_ctx* c, const uint8_t* in_host, int n, float* angles_host, float* logits_host) {
+    if (!c) return fail(WHENET_EINVAL, "null context");
+    c->async_host = true;
+    const int rc = forward_dispatch<true>(c, in_host, n, 0, angles_host, logits_host, 0);
+    c->async_host = false;
+    return rc;
 }
 
 int whenet_forward_f32(whenet_ctx* c, const float* in, int n, int in_is_device, float* angles, float* logits, int out_is_device) {
@@ -1060,6 +1099,7 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!strcmp(key, "stem_variant")) { c->stem_variant = value; return 0; }
     if (!strcmp(key, "pw_variant")) { c->pw_variant = value; return 0; }
     if (!strcmp(key, "k1_variant")) { c->k1_variant = value; return 0; }
+    if (!strcmp(key, "dw1_fused")) { c->dw1_fused = value; return 0; }
     if (!strcmp(key, "k1t_max_block")) { c->k1t_max_block = value; return 0; }
     if (!strcmp(key, "pw_stage_cap")) { c->pw_stage_cap = value; return 0; }
     if (!strcmp(key, "pw_smem_kb")) { c->pw_smem_kb = value; return 0; }

@@ -196,6 +196,17 @@ class WHENet:
             out = (ang[:, 0].copy(), ang[:, 1].copy(), ang[:, 2].copy())
             return out + (d_crops.cpu().numpy(),) if return_crops else out
 
+    def forward_host_to_device(self, crops_u8, angles_out, logits_out=None, n: Optional[int] = None):
+        """Pinned host crops in, DEVICE angles out; asynchronous (H2D on the copy stream, double-buffered across calls)."""
+        n = int(crops_u8.shape[0]) if n is None else int(n)
+        check(self._L.whenet_forward_u8(self._h, _ptr(crops_u8), n, 0, _ptr(angles_out), _ptr(logits_out), 1))
+
+    def forward_host_async(self, crops_u8, angles_out, logits_out=None, n: Optional[int] = None):
+        """Queue H2D + forward + D2H for PINNED host buffers and return; at most two calls in flight, call
+        ``synchronize()`` before reading the outputs.  Consecutive calls overlap upload and compute."""
+        n = int(crops_u8.shape[0]) if n is None else int(n)
+        check(self._L.whenet_forward_u8_async(self._h, _ptr(crops_u8), n, _ptr(angles_out), _ptr(logits_out)))
+
     def set_stream(self, stream_ptr: Optional[int]):
         """Run on a caller-owned CUDA stream.  ``0`` (torch's default stream) is passed as
         cudaStreamLegacy (handle 0x1) because a NULL handle means "back to the internal stream";

@@ -89,6 +89,12 @@ int whenet_set_stream(whenet_ctx* ctx, void* cuda_stream);
 int whenet_forward_u8(whenet_ctx* ctx, const uint8_t* nhwc_rgb, int n, int in_is_device,
                       float* angles_out, float* logits_out, int out_is_device);
 
+/* Asynchronous form of whenet_forward_u8 for HOST buffers (both must be pinned, see whenet_host_alloc): queues the
+ * H2D copy (copy stream), the forward and the D2H of the results, then returns.  Up to TWO calls may be in flight
+ * (input staging and result buffers are double-buffered), so the upload of batch i+1 overlaps the compute of batch i.
+ * Call whenet_synchronize before reading `angles_host` / `logits_host` or reusing `in_host`. */
+int whenet_forward_u8_async(whenet_ctx* ctx, const uint8_t* in_host, int n, float* angles_host, float* logits_host);
+
 /* replaces: self.model.predict(img, batch_size=8), reference whenet.py:27, for
  * an already normalised float32 n x 224 x 224 x 3 input. */
 int whenet_forward_f32(whenet_ctx* ctx, const float* nhwc_normalised, int n, int in_is_device,

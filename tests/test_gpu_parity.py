@@ -346,6 +346,25 @@ def test_cuda_graph_replay(sample_crops, jitter_crops):
     m.close()
 
 
+def test_async_host_double_buffering(sample_crops, jitter_crops):
+    """whenet_forward_u8_async: two host batches in flight, results identical to the synchronous call."""
+    import torch
+    import whenet_b200
+    m = whenet_b200.WHENet(SNAP, device=0, precision="bf16", max_batch=8)
+    a = torch.from_numpy(np.concatenate([sample_crops, jitter_crops])).pin_memory()
+    b = torch.from_numpy(np.concatenate([jitter_crops, sample_crops])).pin_memory()
+    ra = np.stack(m.get_angle(a.numpy()), axis=1)
+    rb = np.stack(m.get_angle(b.numpy()), axis=1)
+    oa = torch.empty((8, 3), dtype=torch.float32).pin_memory()
+    ob = torch.empty((8, 3), dtype=torch.float32).pin_memory()
+    for _ in range(3):
+        m.forward_host_async(a, oa)
+        m.forward_host_async(b, ob)
+        m.synchronize()
+        assert np.array_equal(oa.numpy(), ra) and np.array_equal(ob.numpy(), rb)
+    m.close()
+
+
 def test_device_resident_async(sample_crops):
     import torch
     import whenet_b200
