@@ -283,8 +283,17 @@ def main():
         dname, d = dom
         achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
         es = 4 if args.precision == "fp32" else 2
+        traffic, traffic_note = None, None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath) and args.precision == "bf16" and B == 512:
+            with open(tpath) as f:
+                tj = json.load(f)
+            if dname in tj:
+                traffic = tj[dname]["dram_bytes"]
+                traffic_note = "ncu dram bytes of launch %s (its algorithmic bytes: %d); %s" % (
+                    tj[dname]["launch"], tj[dname]["algorithmic_bytes"], tj["note"])
         roof = {"kernel": dname, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "traffic_note": traffic_note, "peak_source": pk["source"],
                 "share_of_step": d["ms"] / tot_ms, "launches_per_step": d["launches"] / KP,
                 "ms_per_launch_avg": d["ms"] / d["launches"],
                 "tflops": d["flops"] / (d["ms"] * 1e-3) / 1e12,
