@@ -646,8 +646,8 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
     c->max_batch = max_batch;
     c->precision = precision;
     const char* ev = getenv("WHENET_CHUNK");
-    int chunk = ev ? atoi(ev) : 128;
-    if (chunk < 1) chunk = 128;
+    int chunk = ev ? atoi(ev) : max_batch;   // one pass over the whole batch is fastest (8.2 ms vs 13 ms per 512 crops at chunk 128)
+    if (chunk < 1) chunk = max_batch;
     c->chunk = std::min(chunk, max_batch);
     c->use_tc = precision != WHENET_PRECISION_FP32;
     if (const char* e2 = getenv("WHENET_TC")) c->use_tc = atoi(e2) && precision != WHENET_PRECISION_FP32;
