@@ -55,6 +55,7 @@ struct K1Params {
     int spr_log2;          // log2(strips per output row)
     uint32_t idesc;
     int smem_A, smem_W, smem_C, smem_E;   // region sizes in bytes (W and C are per buffer; both double-buffered)
+    int chunks_per_cta;    // grid.z CTAs share one tile, each takes this many consecutive chunks (small batches: more CTAs per crop)
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
@@ -198,7 +199,9 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    prefetch_chunk(0, 0);
+    const int ch_begin = blockIdx.z * p.chunks_per_cta;
+    const int ch_end = min(p.n_chunks, ch_begin + p.chunks_per_cta);
+    prefetch_chunk(ch_begin, ch_begin & 1);
 
     // ---- per-thread constants of the two compute phases
     // epilogue 1: warp w reads TMEM lane quadrant (w & 3); warps 0-3 take the low 16-column units, 4-7 the high ones
@@ -250,16 +253,16 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
     __syncthreads();
     if (!NOEXP && tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        issue_mma(0);
+        issue_mma(ch_begin & 1);
     }
 
-    for (int ch = 0; ch < p.n_chunks; ++ch) {
+    for (int ch = ch_begin; ch < ch_end; ++ch) {
         const int buf = ch & 1;
         const int cbase = ch * p.CC;
         // next chunk's W + constants stream in behind the epilogue / depthwise of this one
-        if (ch + 1 < p.n_chunks) prefetch_chunk(ch + 1, buf ^ 1);
+        if (ch + 1 < ch_end) prefetch_chunk(ch + 1, buf ^ 1);
         if (!NOEXP) {
-            if (!tc::mbar_wait(&mbar, ch & 1)) s_abort = 1;      // MMA(ch): issued one phase ago, normally long done
+            if (!tc::mbar_wait(&mbar, (ch - ch_begin) & 1)) s_abort = 1;      // MMA(ch): issued one phase ago, normally long done
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const bool ok = !s_abort;
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (!NOEXP && tid == 0 && ch + 1 < p.n_chunks && !s_abort) {
+        if (!NOEXP && tid == 0 && ch + 1 < ch_end && !s_abort) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             issue_mma(buf ^ 1);
         }
@@ -381,7 +384,7 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
     if (p.se_counter) {
         if (tid == 0) {
             const int ticket = atomicAdd(p.se_counter + n, 1);
-            s_last = ticket == (int)gridDim.x - 1;
+            s_last = ticket == (int)(gridDim.x * gridDim.z) - 1;
             if (s_last) p.se_counter[n] = 0;
         }
         __syncthreads();
@@ -408,6 +411,7 @@ inline bool plan_k1_candidate(int Hin, int Ho, int Cin, int Cexp, int k, int s, 
     p->cpr = ((Cin >> 3) + 1 + 1) & ~1;
     p->nkb = (p->cpr + 7) / 8;
     p->CC = CC; p->n_chunks = Cexp / CC;
+    p->chunks_per_cta = p->n_chunks;
     int cols = 32;
     while (cols < p->mtiles * CC) cols <<= 1;
     p->tmem_cols = cols;
@@ -479,7 +483,7 @@ inline bool plan_dw_only(int Hin, int C, int k, int s, int pad, K1Params* p, siz
     p->pitchE = C * 2 + 16;
     p->PY = 256 / (C / 4);
     p->spr_log2 = 1;
-    p->smem_A = 0; p->smem_W = 0;
+    p->smem_A = 0; p->smem_W = 0; p->chunks_per_cta = 1;
     p->smem_C = (((k * k + 1) * C * 4) + 1023) & ~1023;
     p->smem_E = (((16 * 16 + 7 + 16) * p->pitchE) + 1023) & ~1023;
     *smem_out = (size_t)2 * p->smem_C + p->smem_E + (size_t)p->PY * C * 4 + 1024;
@@ -488,7 +492,7 @@ inline bool plan_dw_only(int Hin, int C, int k, int s, int pad, K1Params* p, siz
 
 template <typename T>
 int launch_dw_only(cudaStream_t stream, const K1Params& p, size_t smem, int n_crops) {
-    dim3 grid(p.tiles_x * p.tiles_y, n_crops);
+    dim3 grid(p.tiles_x * p.tiles_y, n_crops, 1);
     auto kfn = k1_expand_dw_kernel<T, 3, 1, 7, true>;
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
     kfn<<<grid, 256, smem, stream>>>(p);
@@ -497,7 +501,7 @@ int launch_dw_only(cudaStream_t stream, const K1Params& p, size_t smem, int n_cr
 
 template <typename T>
 int launch_k1(cudaStream_t stream, const K1Params& p, int k, int s, int R, size_t smem, int n_crops) {
-    dim3 grid(p.tiles_x * p.tiles_y, n_crops);
+    dim3 grid(p.tiles_x * p.tiles_y, n_crops, (p.n_chunks + p.chunks_per_cta - 1) / p.chunks_per_cta);
 #define K1(KS, S, RR)                                                                                            \
     do {                                                                                                         \
         auto kfn = k1_expand_dw_kernel<T, KS, S, RR>;                                                            \

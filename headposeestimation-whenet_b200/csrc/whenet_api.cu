@@ -419,6 +419,13 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
                 p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial;
                 p.w_se1t = w.w_se1t; p.b_se1 = w.b_se1; p.w_se2 = w.w_se2; p.b_se2 = w.b_se2; p.gate = c->d_gate; p.Cse = b.cse;
                 p.se_counter = c->se_fused ? c->d_se_counter : nullptr;
+                // small batches: spread one crop's chunks over several CTAs until the grid covers the SMs about twice
+                {
+                    const long long ctas = (long long)p.tiles_x * p.tiles_y * nb;
+                    int split = 1;
+                    while (split < p.n_chunks && ctas * split < 296) ++split;
+                    p.chunks_per_cta = (p.n_chunks + split - 1) / split;
+                }
                 snprintf(nm, sizeof nm, "b%02d.k1", b.idx);
                 Scope sc(c, nm, (double)nb * ((double)b.hin * b.hin * b.cin + (double)b.hout * b.hout * b.cexp) * sizeof(T),
                          2.0 * nb * ((double)b.hin * b.hin * b.cin * b.cexp + (double)b.hout * b.hout * b.k * b.k * b.cexp));
