@@ -548,6 +548,70 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
     se_gate_crop<false>(partial + (long long)n * tiles * C, tiles, inv_hw, w1t, b1, w2, b2, gate + (long long)n * C, C, Cse, sm);
 }
 
+// SE gate, CPB crops per CTA: the two FC weight matrices (up to 2 x 221 KB at C=1152) are read once per CTA and reused
+// for all of its crops instead of once per crop (se_gate_kernel re-streams them 512 times from L2 at N=512).
+// Per crop the arithmetic and its order are exactly those of se_gate_crop, so results do not depend on the grouping.
+template <int CPB>
+__global__ void __launch_bounds__(256) se_gate_multi_kernel(const float* __restrict__ partial, int tiles, float inv_hw,
+                                                            const float* __restrict__ w1t, const float* __restrict__ b1,
+                                                            const float* __restrict__ w2, const float* __restrict__ b2,
+                                                            float* __restrict__ gate, int C, int Cse, int ncrops) {
+    extern __shared__ float sm[];            // mean[CPB][C] | hid[CPB][Cse]
+    float* mean = sm;
+    float* hid = sm + CPB * C;
+    const int tid = threadIdx.x;
+    const int crop0 = blockIdx.x * CPB;
+    const int nc = min(CPB, ncrops - crop0);
+    for (int idx = tid; idx < nc * C; idx += 256) {
+        const int q = idx / C, c = idx - q * C;
+        const float* pn = partial + (long long)(crop0 + q) * tiles * C + c;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int t = 0;
+        for (; t + 3 < tiles; t += 4) {
+            const float* p4 = pn + (long long)t * C;
+            s0 += p4[0]; s1 += p4[C]; s2 += p4[2 * C]; s3 += p4[3 * C];
+        }
+        for (; t < tiles; ++t) s0 += pn[(long long)t * C];
+        mean[q * C + c] = ((s0 + s1) + (s2 + s3)) * inv_hw;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int j = warp; j < Cse; j += 8) {
+        float acc[CPB];
+#pragma unroll
+        for (int q = 0; q < CPB; ++q) acc[q] = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float w = w1t[(long long)j * C + c];
+#pragma unroll
+            for (int q = 0; q < CPB; ++q)
+                if (q < nc) acc[q] = fmaf(mean[q * C + c], w, acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < CPB; ++q) {
+            float s = acc[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0 && q < nc) hid[q * Cse + j] = swish_f(s + b1[j]);
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += 256) {
+        float s[CPB];
+        const float bb = b2[c];
+#pragma unroll
+        for (int q = 0; q < CPB; ++q) s[q] = bb;
+        for (int j = 0; j < Cse; ++j) {
+            const float w = w2[(long long)j * C + c];
+#pragma unroll
+            for (int q = 0; q < CPB; ++q)
+                if (q < nc) s[q] = fmaf(hid[q * Cse + j], w, s[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < CPB; ++q)
+            if (q < nc) gate[(long long)(crop0 + q) * C + c] = sigmoid_f(s[q]);
+    }
+}
+
 // ----------------------------------------------------------------------------- head: GAP + 3 Dense + softmax + expectation
 // feat: [N][49][1280] (post BN+swish head conv), or pooled sums when POOLED.
 // One CTA per crop.  angles[n] = {yaw, pitch, roll}; logits optional [N][252].

@@ -146,6 +146,7 @@ struct whenet_ctx {
     void *bufA = nullptr, *bufB = nullptr, *bufE = nullptr, *bufD = nullptr;
     float *d_partial = nullptr, *d_gate = nullptr, *d_angles = nullptr, *d_logits = nullptr, *d_pooled = nullptr;
     int* d_se_counter = nullptr;   // per-crop tickets of the fused SE excite (zero between kernels)
+    int se_variant = 1;            // 1 = eight crops per CTA share one pass over the SE weights (when the batch is large enough)
     int se_fused = 0;              // K1's/K0's last CTA per crop computes the SE gate (no se_gate launch).  Measured on
                                    // B200 (round 1): the fence + ticket tail costs more (+0.7 ms / 512 crops) than the 15
                                    // small se_gate launches it saves (0.37 ms), so it is off by default.
@@ -453,8 +454,12 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
         if (!(did_k1 && c->se_fused && c->k1_variant == 1)) {
             snprintf(nm, sizeof nm, "b%02d.se", b.idx);
             Scope sc(c, nm, (double)nb * (tiles + 1) * b.cexp * 4.0, 4.0 * nb * b.cexp * b.cse);
-            whenet::se_gate_kernel<<<nb, 256, (b.cexp + b.cse) * sizeof(float), c->stream>>>(
-                c->d_partial, tiles, 1.0f / (float)(b.hout * b.hout), w.w_se1t, w.b_se1, w.w_se2, w.b_se2, c->d_gate, b.cexp, b.cse);
+            if (c->se_variant == 1 && nb >= 64)
+                whenet::se_gate_multi_kernel<8><<<(nb + 7) / 8, 256, 8 * (b.cexp + b.cse) * sizeof(float), c->stream>>>(
+                    c->d_partial, tiles, 1.0f / (float)(b.hout * b.hout), w.w_se1t, w.b_se1, w.w_se2, w.b_se2, c->d_gate, b.cexp, b.cse, nb);
+            else
+                whenet::se_gate_kernel<<<nb, 256, (b.cexp + b.cse) * sizeof(float), c->stream>>>(
+                    c->d_partial, tiles, 1.0f / (float)(b.hout * b.hout), w.w_se1t, w.b_se1, w.w_se2, w.b_se2, c->d_gate, b.cexp, b.cse);
             CK(cudaGetLastError());
         }
         snprintf(nm, sizeof nm, "b%02d.project", b.idx);
@@ -491,7 +496,7 @@ void drop_graphs(whenet_ctx* c) {
 }
 
 int options_signature(const whenet_ctx* c) {
-    return c->chunk * 1000003 + c->dw1_fused * 3 + c->k1_variant * 16384 + c->k1t_max_block * 65536 + c->use_k0 * 8192 + c->se_fused * 4096 + c->use_tc * 64 + c->dw_variant * 32 + c->use_fused * 16 + c->stem_variant * 8 + c->pw_variant * 2 + c->fused_max_block * 128;
+    return c->chunk * 1000003 + c->se_variant * 5 + c->dw1_fused * 3 + c->k1_variant * 16384 + c->k1t_max_block * 65536 + c->use_k0 * 8192 + c->se_fused * 4096 + c->use_tc * 64 + c->dw_variant * 32 + c->use_fused * 16 + c->stem_variant * 8 + c->pw_variant * 2 + c->fused_max_block * 128;
 }
 
 template <typename T, bool IN_U8>
@@ -1099,6 +1104,7 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!c || !key) return fail(WHENET_EINVAL, "bad arguments");
     if (!strcmp(key, "tensor_cores")) { c->use_tc = value && c->precision != WHENET_PRECISION_FP32; return 0; }
     if (!strcmp(key, "se_fused")) { c->se_fused = value; return 0; }
+    if (!strcmp(key, "se_variant")) { c->se_variant = value; return 0; }
     if (!strcmp(key, "k0")) { c->use_k0 = value && c->precision != WHENET_PRECISION_FP32; return 0; }
     if (!strcmp(key, "host_chunk")) { if (value < 1) return fail(WHENET_EINVAL, "host_chunk must be >= 1"); c->host_chunk = value; return 0; }
     if (!strcmp(key, "graph")) { c->use_graph = value; if (!value) drop_graphs(c); return 0; }
