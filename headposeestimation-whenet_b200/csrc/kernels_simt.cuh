@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(256) dw_strip_kernel(const T* __restrict__ in,
 // Device function for ONE crop, executed by a whole 256-thread CTA: the stand-alone kernel below and the tail of
 // K1 (the last CTA of a crop to finish) both call it.  `sm` = C + Cse floats of shared memory.
 // `partial` is read with ld.global.cg: it may have been written by other CTAs of the same launch.
-template <bool COHERENT>
+template <bool COHERENT, int NT = 256>
 __device__ __forceinline__ void se_gate_crop(const float* __restrict__ partial_n, int tiles, float inv_hw,
                                              const float* __restrict__ w1t, const float* __restrict__ b1,
                                              const float* __restrict__ w2, const float* __restrict__ b2,
@@ -506,7 +506,7 @@ __device__ __forceinline__ void se_gate_crop(const float* __restrict__ partial_n
     float* mean = sm;
     float* hid = sm + C;
     const int tid = threadIdx.x;
-    for (int c = tid; c < C; c += 256) {
+    for (int c = tid; c < C; c += NT) {
         // four independent partial chains keep several loads in flight; the association order is fixed (t mod 4), so
         // the sum stays bitwise reproducible
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -521,7 +521,7 @@ __device__ __forceinline__ void se_gate_crop(const float* __restrict__ partial_n
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
-    for (int j = warp; j < Cse; j += 8) {
+    for (int j = warp; j < Cse; j += NT / 32) {
         float s = 0.f;
         for (int c = lane; c < C; c += 32) s = fmaf(mean[c], w1t[(long long)j * C + c], s);
 #pragma unroll
@@ -529,14 +529,15 @@ __device__ __forceinline__ void se_gate_crop(const float* __restrict__ partial_n
         if (lane == 0) hid[j] = swish_f(s + b1[j]);
     }
     __syncthreads();
-    for (int c = tid; c < C; c += 256) {
+    for (int c = tid; c < C; c += NT) {
         float s = b2[c];
         for (int j = 0; j < Cse; ++j) s = fmaf(hid[j], w2[(long long)j * C + c], s);
         gate_n[c] = sigmoid_f(s);
     }
 }
 
-__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ partial, int tiles, float inv_hw,
+template <int NT>
+__global__ void __launch_bounds__(NT) se_gate_kernel(const float* __restrict__ partial, int tiles, float inv_hw,
                                                       const float* __restrict__ w1t,  // [Cse][C]
                                                       const float* __restrict__ b1,   // [Cse]
                                                       const float* __restrict__ w2,   // [Cse][C]
@@ -545,7 +546,7 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
                                                       int C, int Cse) {
     extern __shared__ float sm[];   // mean[C] | hid[Cse]
     const int n = blockIdx.x;
-    se_gate_crop<false>(partial + (long long)n * tiles * C, tiles, inv_hw, w1t, b1, w2, b2, gate + (long long)n * C, C, Cse, sm);
+    se_gate_crop<false, NT>(partial + (long long)n * tiles * C, tiles, inv_hw, w1t, b1, w2, b2, gate + (long long)n * C, C, Cse, sm);
 }
 
 // SE gate, CPB crops per CTA: the two FC weight matrices (up to 2 x 221 KB at C=1152) are read once per CTA and reused

@@ -637,6 +637,8 @@ int launch_pw_tc2(cudaStream_t stream, const T* A, const void* Wt16, const float
     const size_t out_bytes = (size_t)BM * ((size_t)(n_tile >> 3) | 1) * 16;
     int n_stages = nkb < 4 ? nkb : 4;
     if (stage_cap > 0 && n_stages > stage_cap) n_stages = stage_cap;
+    // a grid that does not even fill the SMs once (single-crop latency path) gains nothing from co-residency: deepest ring
+    if (m_tiles * ((N + n_tile - 1) / n_tile) < 148) smem_budget_kb = 180;
     // ring depth vs co-residency: a shallower ring lets more CTAs share the SM (budget = smem per CTA)
     while (n_stages > 2 && n_stages * stage_bytes + gate_bytes > (size_t)smem_budget_kb * 1024) --n_stages;
     size_t smem = n_stages * stage_bytes + gate_bytes;

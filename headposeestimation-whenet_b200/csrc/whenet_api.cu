@@ -146,7 +146,8 @@ struct whenet_ctx {
     void *bufA = nullptr, *bufB = nullptr, *bufE = nullptr, *bufD = nullptr;
     float *d_partial = nullptr, *d_gate = nullptr, *d_angles = nullptr, *d_logits = nullptr, *d_pooled = nullptr;
     int* d_se_counter = nullptr;   // per-crop tickets of the fused SE excite (zero between kernels)
-    int se_variant = 1;            // 1 = eight crops per CTA share one pass over the SE weights (when the batch is large enough)
+    int se_variant = 0;            // 1 = eight crops per CTA share one pass over the SE weights; measured SLOWER on B200
+                                   // (0.71 vs 0.47 ms per 512 crops: 64 fat CTAs lose to 512 thin ones), kept as an option
     int se_fused = 0;              // K1's/K0's last CTA per crop computes the SE gate (no se_gate launch).  Measured on
                                    // B200 (round 1): the fence + ticket tail costs more (+0.7 ms / 512 crops) than the 15
                                    // small se_gate launches it saves (0.37 ms), so it is off by default.
@@ -454,12 +455,17 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
         if (!(did_k1 && c->se_fused && c->k1_variant == 1)) {
             snprintf(nm, sizeof nm, "b%02d.se", b.idx);
             Scope sc(c, nm, (double)nb * (tiles + 1) * b.cexp * 4.0, 4.0 * nb * b.cexp * b.cse);
+            const float inv_hw = 1.0f / (float)(b.hout * b.hout);
+            const size_t se_smem = (b.cexp + b.cse) * sizeof(float);
             if (c->se_variant == 1 && nb >= 64)
-                whenet::se_gate_multi_kernel<8><<<(nb + 7) / 8, 256, 8 * (b.cexp + b.cse) * sizeof(float), c->stream>>>(
-                    c->d_partial, tiles, 1.0f / (float)(b.hout * b.hout), w.w_se1t, w.b_se1, w.w_se2, w.b_se2, c->d_gate, b.cexp, b.cse, nb);
+                whenet::se_gate_multi_kernel<8><<<(nb + 7) / 8, 256, 8 * se_smem, c->stream>>>(
+                    c->d_partial, tiles, inv_hw, w.w_se1t, w.b_se1, w.w_se2, w.b_se2, c->d_gate, b.cexp, b.cse, nb);
+            else if (nb < 64)     // few crops: 32 warps per crop cut the FC latency chain (single-crop latency path)
+                whenet::se_gate_kernel<1024><<<nb, 1024, se_smem, c->stream>>>(
+                    c->d_partial, tiles, inv_hw, w.w_se1t, w.b_se1, w.w_se2, w.b_se2, c->d_gate, b.cexp, b.cse);
             else
-                whenet::se_gate_kernel<<<nb, 256, (b.cexp + b.cse) * sizeof(float), c->stream>>>(
-                    c->d_partial, tiles, 1.0f / (float)(b.hout * b.hout), w.w_se1t, w.b_se1, w.w_se2, w.b_se2, c->d_gate, b.cexp, b.cse);
+                whenet::se_gate_kernel<256><<<nb, 256, se_smem, c->stream>>>(
+                    c->d_partial, tiles, inv_hw, w.w_se1t, w.b_se1, w.w_se2, w.b_se2, c->d_gate, b.cexp, b.cse);
             CK(cudaGetLastError());
         }
         snprintf(nm, sizeof nm, "b%02d.project", b.idx);
