@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
                 sts128(sA + (uint32_t)((kchunks + 1) >> 3) * rows_total * 128 + sw128(rr, (kchunks + 1) & 7), zero);
         }
     }
-    // ---- prefetch of a W chunk + the depthwise constants of a chunk into buffer `buf`
-    auto prefetch_chunk = [&](int ch, int buf) {
+    // ---- cp.async prefetch of a W chunk / of a chunk's depthwise constants into buffer `buf` (the caller commits)
+    auto prefetch_w = [&](int ch, int buf) {
         const int cbase = ch * p.CC;
         const uint32_t w_dst = sW + buf * p.smem_W;
         const int per_row = p.cpr;                                 // data chunks + shift chunk (+ zero pad chunk)
@@ -190,6 +190,9 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
             cp_async16(w_dst + (uint32_t)(c >> 3) * p.CC * 128 + sw128(r, c & 7),
                        valid ? wt + (long long)(cbase + r) * Kaug + c * 8 : wt, valid);
         }
+    };
+    auto prefetch_c = [&](int ch, int buf) {
+        const int cbase = ch * p.CC;
         const uint32_t c_dst = sC + buf * p.smem_C;
         const int q = p.CC >> 2;                                   // 16-byte pieces per constant row
         for (int idx = tid; idx < (KS * KS + 1) * q; idx += 256) {
@@ -197,11 +200,16 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
             const float* src = row == 0 ? p.b_dw + cbase + j * 4 : p.w_dw + (long long)(row - 1) * p.Cexp + cbase + j * 4;
             cp_async16(c_dst + (uint32_t)(row * p.CC + j * 4) * 4, src, true);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
     };
     const int ch_begin = blockIdx.z * p.chunks_per_cta;
     const int ch_end = min(p.n_chunks, ch_begin + p.chunks_per_cta);
-    prefetch_chunk(ch_begin, ch_begin & 1);
+    // W runs TWO chunks ahead (its buffer is free as soon as the MMA that read it has completed), the depthwise
+    // constants one chunk ahead (their buffer is read until the end of the depthwise phase)
+    prefetch_w(ch_begin, ch_begin & 1);
+    prefetch_c(ch_begin, ch_begin & 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (ch_begin + 1 < ch_end) prefetch_w(ch_begin + 1, (ch_begin + 1) & 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
 
     // ---- per-thread constants of the two compute phases
     // epilogue 1: warp w reads TMEM lane quadrant (w & 3); warps 0-3 take the low 16-column units, 4-7 the high ones
@@ -246,8 +254,8 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
         }
         tc::umma_commit(&mbar);
     };
-    // chunk 0: operands (A, W0, constants 0) have to land first
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    // chunk 0: operands (A, W0, constants 0) have to land first (W1 may still be in flight)
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -259,12 +267,15 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
     for (int ch = ch_begin; ch < ch_end; ++ch) {
         const int buf = ch & 1;
         const int cbase = ch * p.CC;
-        // next chunk's W + constants stream in behind the epilogue / depthwise of this one
-        if (ch + 1 < ch_end) prefetch_chunk(ch + 1, buf ^ 1);
         if (!NOEXP) {
             if (!tc::mbar_wait(&mbar, (ch - ch_begin) & 1)) s_abort = 1;      // MMA(ch): issued one phase ago, normally long done
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
+        // constants of chunk ch+1 (group 1), then W of chunk ch+2 into the buffer MMA(ch) has just released (group 2)
+        if (ch + 1 < ch_end) prefetch_c(ch + 1, buf ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (ch + 2 < ch_end) prefetch_w(ch + 2, buf);
+        asm volatile("cp.async.commit_group;" ::: "memory");
         const bool ok = !s_abort;
 
         // ---- epilogue 1: TMEM -> swish -> E (16-bit).  The BN shift is already in the accumulator.
@@ -295,8 +306,9 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
                 }
             }
         }
-        // TMEM(ch) is drained and E(ch) is complete; W(ch+1) has landed -> hand the tensor core its next chunk
-        asm volatile("cp.async.wait_all;" ::: "memory");
+        // TMEM(ch) is drained and E(ch) is complete; W(ch+1) and constants(ch+1) have landed (only the newest group,
+        // W(ch+2), may still be in flight) -> hand the tensor core its next chunk
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();

@@ -146,6 +146,7 @@ struct whenet_ctx {
     void *bufA = nullptr, *bufB = nullptr, *bufE = nullptr, *bufD = nullptr;
     float *d_partial = nullptr, *d_gate = nullptr, *d_angles = nullptr, *d_logits = nullptr, *d_pooled = nullptr;
     int* d_se_counter = nullptr;   // per-crop tickets of the fused SE excite (zero between kernels)
+    int se_wide = 0;               // 1024-thread SE gate CTAs also for large batches
     int se_variant = 0;            // 1 = eight crops per CTA share one pass over the SE weights; measured SLOWER on B200
                                    // (0.71 vs 0.47 ms per 512 crops: 64 fat CTAs lose to 512 thin ones), kept as an option
     int se_fused = 0;              // K1's/K0's last CTA per crop computes the SE gate (no se_gate launch).  Measured on
@@ -460,7 +461,7 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
             if (c->se_variant == 1 && nb >= 64)
                 whenet::se_gate_multi_kernel<8><<<(nb + 7) / 8, 256, 8 * se_smem, c->stream>>>(
                     c->d_partial, tiles, inv_hw, w.w_se1t, w.b_se1, w.w_se2, w.b_se2, c->d_gate, b.cexp, b.cse, nb);
-            else if (nb < 64)     // few crops: 32 warps per crop cut the FC latency chain (single-crop latency path)
+            else if (nb < 64 || c->se_wide)     // 32 warps per crop cut the FC latency chain
                 whenet::se_gate_kernel<1024><<<nb, 1024, se_smem, c->stream>>>(
                     c->d_partial, tiles, inv_hw, w.w_se1t, w.b_se1, w.w_se2, w.b_se2, c->d_gate, b.cexp, b.cse);
             else
@@ -1111,6 +1112,7 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!strcmp(key, "tensor_cores")) { c->use_tc = value && c->precision != WHENET_PRECISION_FP32; return 0; }
     if (!strcmp(key, "se_fused")) { c->se_fused = value; return 0; }
     if (!strcmp(key, "se_variant")) { c->se_variant = value; return 0; }
+    if (!strcmp(key, "se_wide")) { c->se_wide = value; return 0; }
     if (!strcmp(key, "k0")) { c->use_k0 = value && c->precision != WHENET_PRECISION_FP32; return 0; }
     if (!strcmp(key, "host_chunk")) { if (value < 1) return fail(WHENET_EINVAL, "host_chunk must be >= 1"); c->host_chunk = value; return 0; }
     if (!strcmp(key, "graph")) { c->use_graph = value; if (!value) drop_graphs(c); return 0; }
