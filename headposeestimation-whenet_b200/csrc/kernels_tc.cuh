@@ -484,7 +484,9 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
         else if (n_stages == 3) asm volatile("cp.async.wait_group 1;" ::: "memory");
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (GATE) {
-            // each thread rescales exactly the chunks it copied itself
+            // the gate rows in sG were copied by ALL threads (group 0): one CTA barrier before their first use.
+            // The operand chunks themselves need none: each thread rescales exactly the chunks it copied itself.
+            if (kb == 0) __syncthreads();
             const int kc0 = kb * 8;
             const int cb = min(8, kchunks - kc0), cbp = (cb + 1) & ~1;
             if (GATE == 1) {
