@@ -234,6 +234,26 @@ def test_dw_variants_agree(prec, sample_crops, jitter_crops):
         assert np.abs(out[0] - out[1]).max() < 1.0
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_repeatability_stress(prec, sample_crops, jitter_crops):
+    """Race detector of last resort: the same inputs, many forwards, several batch sizes, with per-tap profiling on
+    and off (different kernel timing) - every result must be bitwise identical.  (Round 1 had a missing barrier in
+    pw_tc2 between the cp.async of the SE gate rows and their first use; it only showed up intermittently.)"""
+    import whenet_b200
+    crops = np.concatenate([sample_crops, jitter_crops] * 8)[:61]
+    m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=64)
+    for n in (2, 8, 61):
+        ref = np.stack(m.get_angle(crops[:n]), axis=1)
+        for it in range(12):
+            if it == 6:
+                m.enable_profile(True)
+            got = np.stack(m.get_angle(crops[:n]), axis=1)
+            assert np.array_equal(got, ref), (prec, n, it)
+        m.enable_profile(False)
+        m.read_profile()
+    m.close()
+
+
 def test_chunking_invariance(sample_crops, jitter_crops):
     import whenet_b200
     crops = np.concatenate([sample_crops, jitter_crops] * 3)   # 24
