@@ -143,6 +143,10 @@ struct whenet_ctx {
     void* wt_head = nullptr;
     // workspaces
     int ws_chunk = 0;
+    size_t ws_io = 0, ws_ex = 0, ws_dw = 0, ws_part = 0;   // per-crop element counts of the workspace buffers
+    cudaStream_t aux_stream[2] = {nullptr, nullptr};       // two-stream mode: the two half batches run concurrently
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    int n_streams = 1;
     void *bufA = nullptr, *bufB = nullptr, *bufE = nullptr, *bufD = nullptr;
     float *d_partial = nullptr, *d_gate = nullptr, *d_angles = nullptr, *d_logits = nullptr, *d_pooled = nullptr;
     int* d_se_counter = nullptr;   // per-crop tickets of the fused SE excite (zero between kernels)
@@ -275,6 +279,7 @@ int ensure_ws(whenet_ctx* c) {
     for (const K1TPlan& pl : c->k1t)
         if (pl.valid) part = std::max(part, (size_t)pl.p.tiles_x * pl.p.tiles_y * pl.p.Cexp);
     if (c->dw1.valid) part = std::max(part, (size_t)c->dw1.p.tiles_x * c->dw1.p.tiles_y * c->dw1.p.Cexp);
+    c->ws_io = io; c->ws_ex = ex; c->ws_dw = dw; c->ws_part = part;
     CK(cudaMalloc(&c->bufA, ch * io * es));
     CK(cudaMalloc(&c->bufB, ch * io * es));
     CK(cudaMalloc(&c->bufE, ch * ex * es));
@@ -528,6 +533,41 @@ int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* a
         CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     }
     const int64_t launches0 = c->launches;
+    // ---- two-stream mode (device-resident input, one pass): the two half batches run on two streams so that the
+    //      low-occupancy kernels of one half (late K1 blocks: one CTA per SM) share the SMs with kernels of the other
+    if (c->n_streams == 2 && in_is_device && !graphable && !c->taps_on && n <= c->chunk && n >= 64) {
+        const size_t es = esize(c->precision);
+        const int h0 = (n + 1) / 2;
+        struct Saved { void *A, *B, *E, *D; float *part, *gate, *pooled; int* ctr; cudaStream_t s; } sv{c->bufA, c->bufB, c->bufE, c->bufD,
+                                                                                                     c->d_partial, c->d_gate, c->d_pooled, c->d_se_counter, c->stream};
+        CK(cudaEventRecord(c->ev_fork, sv.s));
+        int rc2 = 0;
+        for (int h = 0; h < 2 && rc2 == 0; ++h) {
+            const int off = h ? h0 : 0, nb = h ? n - h0 : h0;
+            CK(cudaStreamWaitEvent(c->aux_stream[h], c->ev_fork, 0));
+            c->stream = c->aux_stream[h];
+            c->bufA = (char*)sv.A + (size_t)off * c->ws_io * es;  c->bufB = (char*)sv.B + (size_t)off * c->ws_io * es;
+            c->bufE = (char*)sv.E + (size_t)off * c->ws_ex * es;  c->bufD = (char*)sv.D + (size_t)off * c->ws_dw * es;
+            c->d_partial = sv.part + (size_t)off * c->ws_part;    c->d_gate = sv.gate + (size_t)off * 1152;
+            c->d_pooled = sv.pooled + (size_t)off * 1280;         c->d_se_counter = sv.ctr + off;
+            rc2 = forward_chunk<T, IN_U8>(c, (const char*)in + (size_t)off * kImgElems * in_es, nb, d_ang + (size_t)off * 3,
+                                          d_log ? d_log + (size_t)off * WHENET_N_LOGITS : nullptr, false);
+            if (rc2 == 0 && cudaEventRecord(c->ev_join[h], c->aux_stream[h]) != cudaSuccess) rc2 = fail(WHENET_ECUDA, "event record failed");
+        }
+        c->bufA = sv.A; c->bufB = sv.B; c->bufE = sv.E; c->bufD = sv.D;
+        c->d_partial = sv.part; c->d_gate = sv.gate; c->d_pooled = sv.pooled; c->d_se_counter = sv.ctr; c->stream = sv.s;
+        if (rc2) return rc2;
+        CK(cudaStreamWaitEvent(c->stream, c->ev_join[0], 0));
+        CK(cudaStreamWaitEvent(c->stream, c->ev_join[1], 0));
+        if (!out_is_device) {
+            CK(cudaMemcpyAsync(angles_out, d_ang, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            if (logits_out)
+                CK(cudaMemcpyAsync(logits_out, d_log, (size_t)n * WHENET_N_LOGITS * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            c->host_pass_ctr++;
+            if (!c->async_host) CK(cudaStreamSynchronize(c->stream));
+        }
+        return 0;
+    }
     const int step = in_is_device ? c->chunk : std::max(1, std::min(c->chunk, c->host_chunk));
     int ci = 0;
     for (int off = 0; off < n; off += step, ++ci) {
@@ -695,7 +735,10 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
     CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
+        CK(cudaStreamCreateWithFlags(&c->aux_stream[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
     }
@@ -1110,6 +1153,7 @@ int64_t whenet_launch_count(whenet_ctx* c) { return c ? c->launches : 0; }
 int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!c || !key) return fail(WHENET_EINVAL, "bad arguments");
     if (!strcmp(key, "tensor_cores")) { c->use_tc = value && c->precision != WHENET_PRECISION_FP32; return 0; }
+    if (!strcmp(key, "streams")) { c->n_streams = value == 2 ? 2 : 1; return 0; }
     if (!strcmp(key, "se_fused")) { c->se_fused = value; return 0; }
     if (!strcmp(key, "se_variant")) { c->se_variant = value; return 0; }
     if (!strcmp(key, "se_wide")) { c->se_wide = value; return 0; }
@@ -1153,6 +1197,11 @@ void whenet_destroy(whenet_ctx* c) {
         if (c->ev_ready[i]) cudaEventDestroy(c->ev_ready[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
     }
+    for (int i = 0; i < 2; ++i) {
+        if (c->aux_stream[i]) cudaStreamDestroy(c->aux_stream[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;

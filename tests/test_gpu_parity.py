@@ -254,6 +254,24 @@ def test_repeatability_stress(prec, sample_crops, jitter_crops):
     m.close()
 
 
+def test_two_stream_mode_bitwise(sample_crops, jitter_crops):
+    """streams=2 runs the two half batches concurrently on two streams: same bits as the single-stream pass."""
+    import torch
+    import whenet_b200
+    crops = np.concatenate([sample_crops, jitter_crops] * 17)[:131]
+    m = whenet_b200.WHENet(SNAP, device=0, precision="bf16", max_batch=160)
+    ref = np.stack(m.get_angle(crops), axis=1)
+    m.set_option("streams", 2)
+    x = torch.from_numpy(crops).cuda()
+    y = torch.empty((131, 3), dtype=torch.float32, device="cuda")
+    for _ in range(4):
+        y.zero_()
+        m.forward_device(x, y)
+        m.synchronize()
+        assert np.array_equal(y.cpu().numpy(), ref)
+    m.close()
+
+
 def test_chunking_invariance(sample_crops, jitter_crops):
     import whenet_b200
     crops = np.concatenate([sample_crops, jitter_crops] * 3)   # 24
