@@ -144,8 +144,8 @@ struct whenet_ctx {
     // workspaces
     int ws_chunk = 0;
     size_t ws_io = 0, ws_ex = 0, ws_dw = 0, ws_part = 0;   // per-crop element counts of the workspace buffers
-    cudaStream_t aux_stream[2] = {nullptr, nullptr};       // two-stream mode: the two half batches run concurrently
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_half[2] = {nullptr, nullptr};
+    cudaStream_t aux_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // multi-stream mode: batch parts run concurrently
+    cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr}, ev_half[4] = {nullptr, nullptr, nullptr, nullptr};
     int n_streams = 2;   // measured on B200: 67.1k vs 62.6k crops/s at 512 crops (late one-CTA-per-SM kernels share SMs with the other half)
     void *bufA = nullptr, *bufB = nullptr, *bufE = nullptr, *bufD = nullptr;
     float *d_partial = nullptr, *d_gate = nullptr, *d_angles = nullptr, *d_logits = nullptr, *d_pooled = nullptr;
@@ -535,17 +535,19 @@ int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* a
     const int64_t launches0 = c->launches;
     // ---- two-stream mode (device-resident input, one pass): the two half batches run on two streams so that the
     //      low-occupancy kernels of one half (late K1 blocks: one CTA per SM) share the SMs with kernels of the other
-    if (c->n_streams == 2 && !graphable && !c->taps_on && n <= c->chunk && n >= 64) {
+    if (c->n_streams >= 2 && !graphable && !c->taps_on && n <= c->chunk && n >= 64) {
         const size_t es = esize(c->precision);
-        const int h0 = (n + 1) / 2;
+        const int parts = c->n_streams;
+        const int per = (n + parts - 1) / parts;
         struct Saved { void *A, *B, *E, *D; float *part, *gate, *pooled; int* ctr; cudaStream_t s; } sv{c->bufA, c->bufB, c->bufE, c->bufD,
                                                                                                      c->d_partial, c->d_gate, c->d_pooled, c->d_se_counter, c->stream};
         CK(cudaEventRecord(c->ev_fork, sv.s));
         const int slot = in_is_device ? 0 : (int)(c->host_pass_ctr++ & 1u);
         if (!in_is_device) CK(cudaStreamWaitEvent(c->copy_stream, c->ev_free[slot], 0));   // staging slot reusable
         int rc2 = 0;
-        for (int h = 0; h < 2 && rc2 == 0; ++h) {
-            const int off = h ? h0 : 0, nb = h ? n - h0 : h0;
+        for (int h = 0; h < parts && rc2 == 0; ++h) {
+            const int off = h * per, nb = std::min(per, n - off);
+            if (nb <= 0) { CK(cudaEventRecord(c->ev_join[h], c->aux_stream[h])); continue; }
             CK(cudaStreamWaitEvent(c->aux_stream[h], c->ev_fork, 0));
             const void* d_src = (const char*)in + (size_t)off * kImgElems * in_es;
             if (!in_is_device) {
@@ -568,8 +570,7 @@ int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* a
         c->bufA = sv.A; c->bufB = sv.B; c->bufE = sv.E; c->bufD = sv.D;
         c->d_partial = sv.part; c->d_gate = sv.gate; c->d_pooled = sv.pooled; c->d_se_counter = sv.ctr; c->stream = sv.s;
         if (rc2) return rc2;
-        CK(cudaStreamWaitEvent(c->stream, c->ev_join[0], 0));
-        CK(cudaStreamWaitEvent(c->stream, c->ev_join[1], 0));
+        for (int h = 0; h < parts; ++h) CK(cudaStreamWaitEvent(c->stream, c->ev_join[h], 0));
         if (!in_is_device) CK(cudaEventRecord(c->ev_free[slot], c->stream));
         if (!out_is_device) {
             CK(cudaMemcpyAsync(angles_out, d_ang, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -748,10 +749,12 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
         CK(cudaStreamCreateWithFlags(&c->aux_stream[i], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_half[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 2; ++i) {
         CK(cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
     }
@@ -1166,7 +1169,7 @@ int64_t whenet_launch_count(whenet_ctx* c) { return c ? c->launches : 0; }
 int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!c || !key) return fail(WHENET_EINVAL, "bad arguments");
     if (!strcmp(key, "tensor_cores")) { c->use_tc = value && c->precision != WHENET_PRECISION_FP32; return 0; }
-    if (!strcmp(key, "streams")) { c->n_streams = value == 2 ? 2 : 1; return 0; }
+    if (!strcmp(key, "streams")) { c->n_streams = value < 1 ? 1 : (value > 4 ? 4 : value); return 0; }
     if (!strcmp(key, "se_fused")) { c->se_fused = value; return 0; }
     if (!strcmp(key, "se_variant")) { c->se_variant = value; return 0; }
     if (!strcmp(key, "se_wide")) { c->se_wide = value; return 0; }
@@ -1210,7 +1213,7 @@ void whenet_destroy(whenet_ctx* c) {
         if (c->ev_ready[i]) cudaEventDestroy(c->ev_ready[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
         if (c->aux_stream[i]) cudaStreamDestroy(c->aux_stream[i]);
         if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
         if (c->ev_half[i]) cudaEventDestroy(c->ev_half[i]);
