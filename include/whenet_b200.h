@@ -146,9 +146,17 @@ int whenet_profile_read(whenet_ctx* ctx, whenet_kernel_stat* out, int cap);
 /* Kernels launched by this context since creation (the bench's gpu_launches). */
 int64_t whenet_launch_count(whenet_ctx* ctx);
 
-/* Select the kernel family: 0 = CUDA-core fp32-FMA kernels for everything,
- * 1 = tcgen05 tensor-core kernels for the 1x1 convolutions where the storage
- * type allows (bf16/fp16).  Default: 1 for bf16/fp16, 0 for fp32. */
+/* Tuning / ablation switches (all have measured defaults; see DESIGN.md and profiles/README.md):
+ *   "chunk"          crops per pass through the network (default max_batch: one pass)
+ *   "streams"        1..4 batch parts running concurrently on internal streams (default 2)
+ *   "graph"          1: replay device-resident forwards from a captured CUDA graph (default 0)
+ *   "tensor_cores"   0: CUDA-core kernels for every 1x1 conv, 1: tcgen05 (default 1 for bf16/fp16, fp32 is always 0)
+ *   "fused"          1: K1 (expand + depthwise fused, expanded tensor in shared memory) for blocks 2..fused_max_block
+ *   "fused_max_block", "dw1_fused", "k1_variant" (2 = K1T, depthwise on the tensor core), "k1t_max_block",
+ *   "k0" (stem + block-1 depthwise fused), "se_fused", "se_variant", "se_wide",
+ *   "pw_variant" (1 register-staged ring, 2 cp.async ring), "pw_stage_cap", "pw_smem_kb",
+ *   "dw_variant", "stem_variant", "host_chunk".
+ * Unknown keys return WHENET_ENOTFOUND. */
 int whenet_set_option(whenet_ctx* ctx, const char* key, int value);
 
 const char* whenet_last_error(void);
