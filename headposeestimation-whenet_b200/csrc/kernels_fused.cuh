@@ -102,8 +102,12 @@ __device__ __forceinline__ uint32_t sw128(int r, int c) {
 
 // NOEXP: the block has no expand conv (block 1): the halo tile of the block INPUT is copied straight into E and only the
 // depthwise half of the kernel runs (single chunk, no tensor-core work).
-template <typename T, int KS, int S, int R, bool NOEXP = false>
+// CCT != 0 bakes the chunk width (and with it the E row pitch and every constant-table offset) into the code: the
+// depthwise inner loop then addresses shared memory with immediates instead of computed offsets.
+template <typename T, int KS, int S, int R, bool NOEXP = false, int CCT = 0>
 __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) {
+    const int CC = CCT ? CCT : CC;
+    const int pitchE = CCT ? CCT * 2 + 16 : pitchE;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t s_tmem_base;
@@ -143,13 +147,13 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
     if (NOEXP) {
         // ---- E <- the input halo tile itself (Cin == Cexp == CC), zero outside the image (depthwise SAME padding)
         const T* in_n = in + (long long)n * p.Hin * p.Hin * p.Cin;
-        const int cpp = p.CC >> 3;                                  // 16-byte chunks per pixel
+        const int cpp = CC >> 3;                                  // 16-byte chunks per pixel
         for (int idx = tid; idx < npix * cpp; idx += 256) {
             const int r = idx / cpp, c = idx - r * cpp;
             const int ty = r / p.IW, tx = r - ty * p.IW;
             const int iy = iy0 + ty, ix = ix0 + tx;
             const bool valid = iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Hin;
-            cp_async16(sE + (uint32_t)r * p.pitchE + c * 16, valid ? in_n + ((long long)iy * p.Hin + ix) * p.Cin + c * 8 : in_n, valid);
+            cp_async16(sE + (uint32_t)r * pitchE + c * 16, valid ? in_n + ((long long)iy * p.Hin + ix) * p.Cin + c * 8 : in_n, valid);
         }
     }
 
@@ -181,24 +185,24 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
     }
     // ---- cp.async prefetch of a W chunk / of a chunk's depthwise constants into buffer `buf` (the caller commits)
     auto prefetch_w = [&](int ch, int buf) {
-        const int cbase = ch * p.CC;
+        const int cbase = ch * CC;
         const uint32_t w_dst = sW + buf * p.smem_W;
         const int per_row = p.cpr;                                 // data chunks + shift chunk (+ zero pad chunk)
-        for (int idx = tid; idx < (NOEXP ? 0 : p.CC * per_row); idx += 256) {
+        for (int idx = tid; idx < (NOEXP ? 0 : CC * per_row); idx += 256) {
             const int r = idx / per_row, c = idx - r * per_row;
             const bool valid = c <= kchunks;
-            cp_async16(w_dst + (uint32_t)(c >> 3) * p.CC * 128 + sw128(r, c & 7),
+            cp_async16(w_dst + (uint32_t)(c >> 3) * CC * 128 + sw128(r, c & 7),
                        valid ? wt + (long long)(cbase + r) * Kaug + c * 8 : wt, valid);
         }
     };
     auto prefetch_c = [&](int ch, int buf) {
-        const int cbase = ch * p.CC;
+        const int cbase = ch * CC;
         const uint32_t c_dst = sC + buf * p.smem_C;
-        const int q = p.CC >> 2;                                   // 16-byte pieces per constant row
+        const int q = CC >> 2;                                   // 16-byte pieces per constant row
         for (int idx = tid; idx < (KS * KS + 1) * q; idx += 256) {
             const int row = idx / q, j = idx - row * q;
             const float* src = row == 0 ? p.b_dw + cbase + j * 4 : p.w_dw + (long long)(row - 1) * p.Cexp + cbase + j * 4;
-            cp_async16(c_dst + (uint32_t)(row * p.CC + j * 4) * 4, src, true);
+            cp_async16(c_dst + (uint32_t)(row * CC + j * 4) * 4, src, true);
         }
     };
     const int ch_begin = blockIdx.z * p.chunks_per_cta;
@@ -223,15 +227,15 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
         const int iy = iy0 + ty, ix = ix0 + tx;
         e_valid[mt] = mt < p.mtiles && r < npix;
         e_inside[mt] = e_valid[mt] && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Hin;
-        e_row[mt] = sE + (uint32_t)r * p.pitchE;
+        e_row[mt] = sE + (uint32_t)r * pitchE;
     }
-    const int units = p.CC >> 4;
+    const int units = CC >> 4;
     // depthwise: thread = (4-channel vector cv, strip lane py)
-    const int CVc = p.CC >> 2;
+    const int CVc = CC >> 2;
     const int py = tid / CVc, cv = tid - py * CVc;
     const bool dw_active = py < p.PY;
     const int nstrips = p.TH << p.spr_log2;
-    const uint32_t e_rowstride = (uint32_t)p.IW * p.pitchE;
+    const uint32_t e_rowstride = (uint32_t)p.IW * pitchE;
     constexpr int NCOL = (R - 1) * S + KS;
     T* const out_n = out + (long long)n * p.Ho * p.Ho * p.Cexp;
 
@@ -248,8 +252,8 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
             for (int ks = 0; ks < ksteps_total; ++ks) {
                 const int kb = ks >> 2, k = ks & 3;
                 const uint64_t ad = tc::make_desc(sA + (uint32_t)kb * rows_total * 128 + (uint32_t)mt * BM * 128);
-                const uint64_t bd = tc::make_desc(sW + buf * p.smem_W + (uint32_t)kb * p.CC * 128);
-                tc::umma_f16(tmem_d + (uint32_t)(mt * p.CC), ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), p.idesc, ks ? 1u : 0u);
+                const uint64_t bd = tc::make_desc(sW + buf * p.smem_W + (uint32_t)kb * CC * 128);
+                tc::umma_f16(tmem_d + (uint32_t)(mt * CC), ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), p.idesc, ks ? 1u : 0u);
             }
         }
         tc::umma_commit(&mbar);
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
 
     for (int ch = ch_begin; ch < ch_end; ++ch) {
         const int buf = ch & 1;
-        const int cbase = ch * p.CC;
+        const int cbase = ch * CC;
         if (!NOEXP) {
             if (!tc::mbar_wait(&mbar, (ch - ch_begin) & 1)) s_abort = 1;      // MMA(ch): issued one phase ago, normally long done
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
                 if (mt < p.mtiles) {
                     for (int u = (mt * units + half) & 1; u < units; u += 2) {
                         float v[16];
-                        tc::tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mt * p.CC + u * 16), v);
+                        tc::tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mt * CC + u * 16), v);
                         if (e_valid[mt]) {
                             uint4 lo, hi;
                             if (e_inside[mt]) {
@@ -329,18 +333,18 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
                 float acc[R][4];
 #pragma unroll
                 for (int r = 0; r < R; ++r) { acc[r][0] = bq.x; acc[r][1] = bq.y; acc[r][2] = bq.z; acc[r][3] = bq.w; }
-                uint32_t erow = e_cv + (uint32_t)(oyl * S) * e_rowstride + (uint32_t)(oxl0 * S) * p.pitchE;
+                uint32_t erow = e_cv + (uint32_t)(oyl * S) * e_rowstride + (uint32_t)(oxl0 * S) * pitchE;
 #pragma unroll
                 for (int ky = 0; ky < KS; ++ky) {
                     float4 wr[KS];
 #pragma unroll
-                    for (int kx = 0; kx < KS; ++kx) wr[kx] = lds_f4(cst + (uint32_t)((1 + ky * KS + kx) * p.CC) * 4);
+                    for (int kx = 0; kx < KS; ++kx) wr[kx] = lds_f4(cst + (uint32_t)((1 + ky * KS + kx) * CC) * 4);
                     uint32_t ea = erow;
 #pragma unroll
                     for (int col = 0; col < NCOL; ++col) {
                         uint32_t a, b;
                         lds64(ea, a, b);
-                        ea += p.pitchE;
+                        ea += pitchE;
                         float x0, x1, x2, x3;
                         unpack2<T>(a, x0, x1);
                         unpack2<T>(b, x2, x3);
@@ -371,15 +375,15 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
                     }
                 }
             }
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sR + (uint32_t)(py * p.CC + cv * 4) * 4),
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sR + (uint32_t)(py * CC + cv * 4) * 4),
                          "f"(sum[0]), "f"(sum[1]), "f"(sum[2]), "f"(sum[3]) : "memory");
         }
         __syncthreads();
-        if (ok && tid < p.CC) {
+        if (ok && tid < CC) {
             float tot = 0.f;
             for (int y = 0; y < p.PY; ++y) {
                 float t;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(sR + (uint32_t)(y * p.CC + tid) * 4));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(sR + (uint32_t)(y * CC + tid) * 4));
                 tot += t;
             }
             p.partial[((long long)n * gridDim.x + tile) * p.Cexp + cbase + tid] = tot;
@@ -516,7 +520,7 @@ int launch_k1(cudaStream_t stream, const K1Params& p, int k, int s, int R, size_
     dim3 grid(p.tiles_x * p.tiles_y, n_crops, (p.n_chunks + p.chunks_per_cta - 1) / p.chunks_per_cta);
 #define K1(KS, S, RR)                                                                                            \
     do {                                                                                                         \
-        auto kfn = k1_expand_dw_kernel<T, KS, S, RR>;                                                            \
+        auto kfn = p.CC == 48 ? k1_expand_dw_kernel<T, KS, S, RR, false, 48> : k1_expand_dw_kernel<T, KS, S, RR>;  \
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1; \
         kfn<<<grid, 256, smem, stream>>>(p);                                                                     \
         return 0;                                                                                                \
