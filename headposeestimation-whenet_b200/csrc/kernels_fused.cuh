@@ -106,8 +106,8 @@ __device__ __forceinline__ uint32_t sw128(int r, int c) {
 // depthwise inner loop then addresses shared memory with immediates instead of computed offsets.
 template <typename T, int KS, int S, int R, bool NOEXP = false, int CCT = 0>
 __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) {
-    const int CC = CCT ? CCT : CC;
-    const int pitchE = CCT ? CCT * 2 + 16 : pitchE;
+    const int CC = CCT ? CCT : p.CC;
+    const int pitchE = CCT ? CCT * 2 + 16 : p.pitchE;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t s_tmem_base;
