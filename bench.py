@@ -177,6 +177,20 @@ def main():
     for kv in args.opt:
         k, v = kv.split("=")
         net.set_option(k, int(v))
+    # ---- self-check before timing anything: the configuration being measured (fused tcgen05 kernels, two streams) must
+    #      agree with the plain CUDA-core kernel family on the committed Sample/jitter crops.  A fast wrong kernel is
+    #      not a result; the oracle comparison proper lives in tests/ and __graft_entry__.smoke().
+    chk = np.concatenate([np.load(os.path.join(ROOT, "tests", "golden", "sample_crops.npy")),
+                          np.load(os.path.join(ROOT, "tests", "golden", "jitter_crops.npy"))] * 8)
+    got = np.stack(net.get_angle(chk), axis=1)
+    net.set_option("fused", 0); net.set_option("tensor_cores", 0); net.set_option("streams", 1)
+    ref = np.stack(net.get_angle(chk), axis=1)
+    net.set_option("fused", 1); net.set_option("tensor_cores", 1); net.set_option("streams", 2)
+    tol = 0.02 if args.precision == "fp32" else (1.5 if args.precision == "bf16" else 0.3)
+    self_check = float(np.abs(got - ref).max())
+    if not (self_check <= tol):
+        raise SystemExit("bench self-check failed: measured configuration differs from the CUDA-core path by %.3f deg" % self_check)
+
     stream = torch.cuda.Stream()          # a real (non-default) stream shared by the library, NCCL and the timing events
     torch.cuda.set_stream(stream)
     net.set_stream(stream.cuda_stream)
@@ -332,6 +346,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": B * IMG_BYTES, "d2h_bytes_per_step": B * 12,
                         "api": "WHENet.forward_host_to_device + D2H of the angles, two steps in flight (pinned uint8 in, pinned angles out)"},
                 "gpu_launches": int(launches * world),
+                "self_check_max_deg_vs_simt_path": self_check,
                 "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
