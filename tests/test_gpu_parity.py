@@ -254,6 +254,23 @@ def test_repeatability_stress(prec, sample_crops, jitter_crops):
     m.close()
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_full_size_batch_properties(prec, sample_crops, jitter_crops):
+    """BASELINE.json's full single-GPU size (512 crops) through the default configuration (two streams, fused kernels):
+    the oracle is too slow for 512 crops, so use size-independent properties - a batch tiled from 8 distinct crops
+    must be periodic and bitwise equal to the 8-crop result, whatever the position of a crop in the batch."""
+    import whenet_b200
+    base = np.concatenate([sample_crops, jitter_crops])
+    m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=512)
+    small = np.stack(m.get_angle(base), axis=1)
+    rng = np.random.default_rng(7)
+    order = rng.integers(0, 8, 512)
+    big = np.stack(m.get_angle(base[order]), axis=1)
+    assert big.shape == (512, 3)
+    assert np.array_equal(big, small[order])
+    m.close()
+
+
 def test_two_stream_mode_bitwise(sample_crops, jitter_crops):
     """streams=2 runs the two half batches concurrently on two streams: same bits as the single-stream pass."""
     import torch
