@@ -8,7 +8,7 @@ n = int(os.environ.get("N", "128"))
 reps = int(os.environ.get("REPS", "2"))
 m = whenet_b200.WHENet(whenet_b200.weights.DEFAULT_NPZ, device=0, precision=os.environ.get("PREC", "bf16"), max_batch=n)
 m.set_option("chunk", n)
-for k, v in (("tensor_cores", "TC"), ("dw_variant", "DWV"), ("fused", "FUSED")):
+for k, v in (("tensor_cores", "TC"), ("dw_variant", "DWV"), ("fused", "FUSED"), ("streams", "STREAMS")):
     if v in os.environ:
         m.set_option(k, int(os.environ[v]))
 x = np.random.default_rng(0).integers(0, 256, (n, 224, 224, 3), dtype=np.uint8)
