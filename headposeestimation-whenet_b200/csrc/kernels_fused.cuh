@@ -391,7 +391,8 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
         // E, the squeeze scratch and TMEM are reused only after the barrier at the top of the next chunk
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __threadfence();                       // this CTA's squeeze partials are visible device-wide before the ticket
+    if (p.se_counter) __threadfence();     // fused SE only: this CTA's squeeze partials are visible device-wide before the ticket
+                                           // (unconditional, the MEMBAR made every CTA wait out its own output stores)
     __syncthreads();
     if (!NOEXP && warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)p.tmem_cols) : "memory");
