@@ -71,7 +71,7 @@ def load():
     L.whenet_debug_enable_taps.argtypes = [P, C.c_int]
     L.whenet_debug_tap.argtypes = [P, C.c_char_p, P, C.c_size_t, C.POINTER(C.c_size_t)]
     L.whenet_debug_conv1x1.argtypes = [P, C.c_int, P, P, P, P, P, P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int]
-    L.whenet_debug_set_k1_plan.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.whenet_debug_set_k1_plan.argtypes = [P] + [C.c_int] * 7
     L.whenet_profile_enable.argtypes = [P, C.c_int]
     L.whenet_profile_read.argtypes = [P, C.POINTER(KernelStat), C.c_int]
     L.whenet_launch_count.argtypes = [P]

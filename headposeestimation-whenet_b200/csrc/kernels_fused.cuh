@@ -5,14 +5,16 @@
 //   -> depthwise KSxKS stride S, TF-SAME (CUDA-core FMA on the smem tile) -> BN shift + swish
 //   -> D (global, 16-bit) + deterministic SE squeeze partial sums
 //
-// One CTA owns a TH x TW tile of the depthwise OUTPUT of one crop.  The matching input halo tile
-// (IH x IW = (TH-1)*S+KS square, raster order = GEMM rows) is staged once with cp.async in the UMMA
-// K-major SWIZZLE_128B layout; the expanded channels are then produced and consumed CC at a time:
+// One CTA owns a TH x TW tile of the depthwise OUTPUT of one crop (or, where one tile is the whole image, of NB
+// crops).  The matching input halo tile is IH x IW = (TH-1)*S+KS square; only its pixels INSIDE the image become GEMM
+// rows (raster order over the inside rectangle) - the depthwise pads the EXPANDED tensor with zeros, so halo pixels
+// outside the image are plain zero rows of E that are written once and never touched by the tensor core.  The rows are
+// staged once with cp.async in the UMMA K-major SWIZZLE_128B layout; the expanded channels are then produced and
+// consumed CC at a time:
 //
 //   for each chunk of CC expanded channels (W chunk + depthwise constants of chunk i+1 prefetched with cp.async):
 //       tcgen05.mma  D[mt][128 x CC] = [A | 1 1] (128 x (Cin+8)) * [Wc | shift_hi shift_lo]^T   for every 128-row tile mt
-//       TMEM -> registers -> swish, ZERO for halo pixels outside the image (the depthwise pads the EXPANDED
-//               tensor with zeros, not the block input) -> 16-bit -> E[pixel][CC] in smem
+//       TMEM -> registers -> swish -> 16-bit -> E[halo pixel][CC] in smem
 //       depthwise strips straight out of E (ld.shared.v2), the KS weights of one kernel row from smem
 //       -> store D, accumulate the squeeze sums
 //
@@ -21,6 +23,8 @@
 // 1.0 columns, W gets the shift split into a bf16 high and low part (error 2^-17 relative), so the
 // epilogue has no bias loads or adds.
 #pragma once
+#include <algorithm>
+
 #include "kernels_tc.cuh"
 
 namespace whenet {
@@ -46,12 +50,18 @@ struct K1Params {
     int TH, TW, IH, IW;    // output tile, input halo tile
     int tiles_x, tiles_y;
     int CC, n_chunks;      // expanded channels per chunk (multiple of 16), number of chunks
-    int mtiles;            // ceil(IH*IW / 128)  (<= 3)
+    int mtiles;            // most 128-row GEMM tiles any CTA needs (<= 3); sizes TMEM
+    int rows_alloc;        // A rows per K block in smem: most GEMM rows any CTA has, rounded up to 8 (the last M tile's
+                           // UMMA reads on past them into whatever follows - those accumulator rows are never used)
+    int NB;                // crops per CTA (> 1 only when one tile is the whole image)
+    int N;                 // crops in this launch
+    int e_rows;            // E rows per crop (halo pixels + slack)
+    int PYc;               // strip lanes per crop = PY / NB
     int cpr;               // 16-byte chunks per operand row incl. the ones/shift chunk, rounded up to even
     int nkb;               // ceil(cpr / 8)
     int tmem_cols;         // power of two >= mtiles*CC
     int pitchE;            // bytes per E row = CC*2 + 16
-    int PY;                // strip lanes in the depthwise phase = 256 / (CC/4)
+    int PY;                // strip lanes in the depthwise phase = threads / (CC/4), rounded down to a multiple of NB
     int spr_log2;          // log2(strips per output row)
     uint32_t idesc;
     int smem_A, smem_W, smem_C, smem_E;   // region sizes in bytes (W and C are per buffer; both double-buffered)
@@ -100,14 +110,21 @@ __device__ __forceinline__ uint32_t sw128(int r, int c) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
+// exact floor(x / d) for the small non-negative ints of the tile arithmetic (x < 2^14), with inv = 1.0f / d:
+// (x + 0.5) / d is at least 0.5 / d away from every integer, far more than the float rounding error
+__device__ __forceinline__ int div_small(int x, float inv) { return __float2int_rz(((float)x + 0.5f) * inv); }
+
 // NOEXP: the block has no expand conv (block 1): the halo tile of the block INPUT is copied straight into E and only the
 // depthwise half of the kernel runs (single chunk, no tensor-core work).
 // CCT != 0 bakes the chunk width (and with it the E row pitch and every constant-table offset) into the code: the
 // depthwise inner loop then addresses shared memory with immediates instead of computed offsets.
-template <typename T, int KS, int S, int R, bool NOEXP = false, int CCT = 0>
-__global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) {
+// NT = threads per CTA: 256 (two CTAs share an SM) or 512 (one CTA per SM - the late blocks, whose operands do not
+// leave room for two CTAs, get their 16 warps this way).
+template <typename T, int KS, int S, int R, bool NOEXP = false, int CCT = 0, int NT = 256>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(const K1Params p) {
     const int CC = CCT ? CCT : p.CC;
     const int pitchE = CCT ? CCT * 2 + 16 : p.pitchE;
+    constexpr int NG = NT / 128;                                // warp groups of four (one warp per TMEM lane quadrant)
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t s_tmem_base;
@@ -116,24 +133,32 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sA = smem0;                                  // [nkb][mtiles*128 rows][128 B]   swizzled
+    const uint32_t sA = smem0;                                  // [nkb][rows_alloc][128 B]        swizzled
     const uint32_t sW = sA + p.smem_A;                          // 2 x [nkb][CC rows][128 B]       swizzled
     const uint32_t sC = sW + 2 * p.smem_W;                      // 2 x { b_dw[CC], w_dw[KS*KS][CC] } fp32
-    const uint32_t sE = sC + 2 * p.smem_C;                      // [IH*IW rows (+slack)][pitchE]
+    const uint32_t sE = sC + 2 * p.smem_C;                      // [NB][e_rows][pitchE]
     const uint32_t sR = sE + p.smem_E;                          // [PY][CC] fp32 squeeze partials
 
     const T* in = reinterpret_cast<const T*>(p.in);
     const T* wt = reinterpret_cast<const T*>(p.wt_aug);
     T* out = reinterpret_cast<T*>(p.out);
 
-    const int n = blockIdx.y, tile = blockIdx.x;
+    const int n0 = blockIdx.y * p.NB, tile = blockIdx.x;
+    const int nb_here = min(p.NB, p.N - n0);                                       // crops of this CTA
     const int tyi = tile / p.tiles_x;
     const int ty0 = tyi * p.TH, tx0 = (tile - tyi * p.tiles_x) * p.TW;             // output-tile origin
     const int iy0 = ty0 * S - p.pad, ix0 = tx0 * S - p.pad;                       // input-tile origin (may be < 0)
     const int npix = p.IH * p.IW;
-    const int rows_total = p.mtiles * BM;
+    // the part of the halo tile that lies inside the image: these pixels are the GEMM rows
+    const int ty_lo = max(0, -iy0), tx_lo = max(0, -ix0);
+    const int IHin = min(p.IH, p.Hin - iy0) - ty_lo, IWin = min(p.IW, p.Hin - ix0) - tx_lo;
+    const int npix_in = IHin * IWin;
+    const int rows_gemm = nb_here * npix_in;
+    const int mtc = (rows_gemm + BM - 1) / BM;          // M tiles of this CTA (<= p.mtiles)
+    const float inv_IWin = 1.0f / (float)IWin, inv_npix = 1.0f / (float)npix_in;
     const int kchunks = p.Cin >> 3;                     // data chunks per row; chunk `kchunks` holds the ones / the shift
     const int Kaug = p.Cin + 8;
+    const uint32_t a_kb_stride = (uint32_t)p.rows_alloc * 128u;
 
     if (tid == 0) {
         tc::mbar_init(&mbar, 1);
@@ -146,9 +171,9 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
     }
     if (NOEXP) {
         // ---- E <- the input halo tile itself (Cin == Cexp == CC), zero outside the image (depthwise SAME padding)
-        const T* in_n = in + (long long)n * p.Hin * p.Hin * p.Cin;
+        const T* in_n = in + (long long)n0 * p.Hin * p.Hin * p.Cin;
         const int cpp = CC >> 3;                                  // 16-byte chunks per pixel
-        for (int idx = tid; idx < npix * cpp; idx += 256) {
+        for (int idx = tid; idx < npix * cpp; idx += NT) {
             const int r = idx / cpp, c = idx - r * cpp;
             const int ty = r / p.IW, tx = r - ty * p.IW;
             const int iy = iy0 + ty, ix = ix0 + tx;
@@ -157,30 +182,28 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
         }
     }
 
-    // ---- A: the input halo tile (cp.async, zero-filled outside the image), + the ones chunk, + an even-count pad chunk
+    // ---- A: the inside pixels of the halo tile (cp.async), + the ones chunk, + an even-count pad chunk
     if (!NOEXP) {
-        const T* in_n = in + (long long)n * p.Hin * p.Hin * p.Cin;
-        // one (pixel, chunk) item per step; walk pixels with a running (ty, tx) instead of dividing
-        const int items = npix * kchunks;
-        int r = tid / kchunks, c = tid - r * kchunks;
-        int ty = r / p.IW, tx = r - ty * p.IW;
-        const int dr = 256 / kchunks, dc = 256 - dr * kchunks;      // advance of (r, c) per step
-        const int dty = dr / p.IW, dtx = dr - dty * p.IW;
-        for (int idx = tid; idx < items; idx += 256) {
-            const int iy = iy0 + ty, ix = ix0 + tx;
-            const bool valid = iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Hin;
-            const T* src = valid ? in_n + ((long long)iy * p.Hin + ix) * p.Cin + c * 8 : in_n;
-            cp_async16(sA + (uint32_t)(c >> 3) * rows_total * 128 + sw128(r, c & 7), src, valid);
-            c += dc; r += dr; ty += dty; tx += dtx;
-            if (c >= kchunks) { c -= kchunks; ++r; ++tx; }
-            if (tx >= p.IW) { tx -= p.IW; ++ty; }
-            if (tx >= p.IW) { tx -= p.IW; ++ty; }
+        const float inv_kch = 1.0f / (float)kchunks;
+        const T* in_t = in + ((long long)n0 * p.Hin * p.Hin + (long long)(iy0 + ty_lo) * p.Hin + (ix0 + tx_lo)) * p.Cin;
+        const int items = rows_gemm * kchunks;
+        for (int idx = tid; idx < items; idx += NT) {
+            const int r = div_small(idx, inv_kch), c = idx - r * kchunks;
+            const int j = div_small(r, inv_npix), q = r - j * npix_in;
+            const int ty = div_small(q, inv_IWin), tx = q - ty * IWin;
+            const T* src = in_t + ((long long)(j * p.Hin + ty) * p.Hin + tx) * p.Cin + c * 8;
+            cp_async16(sA + (uint32_t)(c >> 3) * a_kb_stride + sw128(r, c & 7), src, true);
         }
         const uint4 ones = make_uint4(ones2<T>(), 0u, 0u, 0u), zero = make_uint4(0u, 0u, 0u, 0u);
-        for (int rr = tid; rr < npix; rr += 256) {
-            sts128(sA + (uint32_t)(kchunks >> 3) * rows_total * 128 + sw128(rr, kchunks & 7), ones);
+        for (int rr = tid; rr < rows_gemm; rr += NT) {
+            sts128(sA + (uint32_t)(kchunks >> 3) * a_kb_stride + sw128(rr, kchunks & 7), ones);
             if (p.cpr > kchunks + 1)
-                sts128(sA + (uint32_t)((kchunks + 1) >> 3) * rows_total * 128 + sw128(rr, (kchunks + 1) & 7), zero);
+                sts128(sA + (uint32_t)((kchunks + 1) >> 3) * a_kb_stride + sw128(rr, (kchunks + 1) & 7), zero);
+        }
+        // halo pixels outside the image: zero rows of E for the whole kernel (epilogue 1 only writes inside rows)
+        if (npix_in != npix) {
+            const int pieces = (p.NB * p.e_rows * pitchE) >> 4;
+            for (int i = tid; i < pieces; i += NT) sts128(sE + (uint32_t)i * 16u, zero);
         }
     }
     // ---- cp.async prefetch of a W chunk / of a chunk's depthwise constants into buffer `buf` (the caller commits)
@@ -188,7 +211,7 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
         const int cbase = ch * CC;
         const uint32_t w_dst = sW + buf * p.smem_W;
         const int per_row = p.cpr;                                 // data chunks + shift chunk (+ zero pad chunk)
-        for (int idx = tid; idx < (NOEXP ? 0 : CC * per_row); idx += 256) {
+        for (int idx = tid; idx < (NOEXP ? 0 : CC * per_row); idx += NT) {
             const int r = idx / per_row, c = idx - r * per_row;
             const bool valid = c <= kchunks;
             cp_async16(w_dst + (uint32_t)(c >> 3) * CC * 128 + sw128(r, c & 7),
@@ -199,7 +222,7 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
         const int cbase = ch * CC;
         const uint32_t c_dst = sC + buf * p.smem_C;
         const int q = CC >> 2;                                   // 16-byte pieces per constant row
-        for (int idx = tid; idx < (KS * KS + 1) * q; idx += 256) {
+        for (int idx = tid; idx < (KS * KS + 1) * q; idx += NT) {
             const int row = idx / q, j = idx - row * q;
             const float* src = row == 0 ? p.b_dw + cbase + j * 4 : p.w_dw + (long long)(row - 1) * p.Cexp + cbase + j * 4;
             cp_async16(c_dst + (uint32_t)(row * CC + j * 4) * 4, src, true);
@@ -216,28 +239,29 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
     asm volatile("cp.async.commit_group;" ::: "memory");
 
     // ---- per-thread constants of the two compute phases
-    // epilogue 1: warp w reads TMEM lane quadrant (w & 3); warps 0-3 take the low 16-column units, 4-7 the high ones
-    const int q4 = warp & 3;
+    // epilogue 1: warp w reads TMEM lane quadrant (w & 3); the NG warp groups share the 16-column units of every M tile
+    const int q4 = warp & 3, grp = warp >> 2;
     uint32_t e_row[3];
-    bool e_inside[3], e_valid[3];
+    bool e_valid[3];
 #pragma unroll
     for (int mt = 0; mt < 3; ++mt) {
         const int r = mt * BM + q4 * 32 + lane;
-        const int ty = r / p.IW, tx = r - ty * p.IW;
-        const int iy = iy0 + ty, ix = ix0 + tx;
-        e_valid[mt] = mt < p.mtiles && r < npix;
-        e_inside[mt] = e_valid[mt] && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Hin;
-        e_row[mt] = sE + (uint32_t)r * pitchE;
+        e_valid[mt] = !NOEXP && r < rows_gemm;
+        const int rc = e_valid[mt] ? r : 0;
+        const int j = div_small(rc, inv_npix), q = rc - j * npix_in;
+        const int ty = div_small(q, inv_IWin), tx = q - ty * IWin;
+        e_row[mt] = sE + (uint32_t)(j * p.e_rows + (ty_lo + ty) * p.IW + tx_lo + tx) * pitchE;
     }
     const int units = CC >> 4;
-    // depthwise: thread = (4-channel vector cv, strip lane py)
+    // depthwise: thread = (4-channel vector cv, strip lane py); with NB crops per CTA the lanes split evenly between them
     const int CVc = CC >> 2;
     const int py = tid / CVc, cv = tid - py * CVc;
-    const bool dw_active = py < p.PY;
+    const int jc = py / p.PYc, pl = py - jc * p.PYc;               // crop of this lane, lane within the crop
+    const bool dw_active = py < p.PY && jc < nb_here;
     const int nstrips = p.TH << p.spr_log2;
     const uint32_t e_rowstride = (uint32_t)p.IW * pitchE;
     constexpr int NCOL = (R - 1) * S + KS;
-    T* const out_n = out + (long long)n * p.Ho * p.Ho * p.Cexp;
+    T* const out_n = out + (long long)(n0 + jc) * p.Ho * p.Ho * p.Cexp;
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -248,10 +272,10 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
     // drained TMEM(ch) and executes while the whole CTA is busy with the depthwise of chunk ch.
     auto issue_mma = [&](int buf) {
         const int ksteps_total = p.cpr >> 1;
-        for (int mt = 0; mt < p.mtiles; ++mt) {
+        for (int mt = 0; mt < mtc; ++mt) {
             for (int ks = 0; ks < ksteps_total; ++ks) {
                 const int kb = ks >> 2, k = ks & 3;
-                const uint64_t ad = tc::make_desc(sA + (uint32_t)kb * rows_total * 128 + (uint32_t)mt * BM * 128);
+                const uint64_t ad = tc::make_desc(sA + (uint32_t)kb * a_kb_stride + (uint32_t)mt * BM * 128);
                 const uint64_t bd = tc::make_desc(sW + buf * p.smem_W + (uint32_t)kb * CC * 128);
                 tc::umma_f16(tmem_d + (uint32_t)(mt * CC), ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), p.idesc, ks ? 1u : 0u);
             }
@@ -283,26 +307,20 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
         const bool ok = !s_abort;
 
         // ---- epilogue 1: TMEM -> swish -> E (16-bit).  The BN shift is already in the accumulator.
-        //      (M tile, 16-column unit) pairs alternate between the two warp halves so both carry the same load.
+        //      (M tile, 16-column unit) pairs go round-robin over the warp groups so all carry the same load;
+        //      a warp whose 32 rows of an M tile are all past the last GEMM row skips the tile.
         if (ok && !NOEXP) {
-            const int half = warp >> 2;
 #pragma unroll
             for (int mt = 0; mt < 3; ++mt) {
-                if (mt < p.mtiles) {
-                    for (int u = (mt * units + half) & 1; u < units; u += 2) {
+                if (mt * BM + q4 * 32 < rows_gemm) {
+                    for (int u = (grp + NG * 8 - mt * units) % NG; u < units; u += NG) {
                         float v[16];
                         tc::tmem_ld16(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mt * CC + u * 16), v);
                         if (e_valid[mt]) {
-                            uint4 lo, hi;
-                            if (e_inside[mt]) {
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] = swish_from_half(v[j]);
-                                lo = make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
-                                hi = make_uint4(pack2<T>(v[8], v[9]), pack2<T>(v[10], v[11]), pack2<T>(v[12], v[13]), pack2<T>(v[14], v[15]));
-                            } else {
-                                lo = make_uint4(0u, 0u, 0u, 0u);
-                                hi = lo;
-                            }
+                            for (int j = 0; j < 16; ++j) v[j] = swish_from_half(v[j]);
+                            const uint4 lo = make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
+                            const uint4 hi = make_uint4(pack2<T>(v[8], v[9]), pack2<T>(v[10], v[11]), pack2<T>(v[12], v[13]), pack2<T>(v[14], v[15]));
                             sts128(e_row[mt] + u * 32, lo);
                             sts128(e_row[mt] + u * 32 + 16, hi);
                         }
@@ -327,8 +345,8 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
             const int c0 = cbase + cv * 4;
             const uint32_t cst = sC + buf * p.smem_C + (uint32_t)cv * 16;         // this thread's column of the constants
             const float4 bq = lds_f4(cst);
-            const uint32_t e_cv = sE + (uint32_t)cv * 8;
-            for (int sidx = py; sidx < nstrips; sidx += p.PY) {
+            const uint32_t e_cv = sE + (uint32_t)(jc * p.e_rows) * pitchE + (uint32_t)cv * 8;
+            for (int sidx = pl; sidx < nstrips; sidx += p.PYc) {
                 const int oyl = sidx >> p.spr_log2, oxl0 = (sidx - (oyl << p.spr_log2)) * R;
                 float acc[R][4];
 #pragma unroll
@@ -379,14 +397,17 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
                          "f"(sum[0]), "f"(sum[1]), "f"(sum[2]), "f"(sum[3]) : "memory");
         }
         __syncthreads();
-        if (ok && tid < CC) {
-            float tot = 0.f;
-            for (int y = 0; y < p.PY; ++y) {
-                float t;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(sR + (uint32_t)(y * CC + tid) * 4));
-                tot += t;
+        if (ok && tid < p.NB * CC) {
+            const int jj = tid / CC, cc = tid - jj * CC;
+            if (jj < nb_here) {
+                float tot = 0.f;
+                for (int y = jj * p.PYc; y < (jj + 1) * p.PYc; ++y) {
+                    float t;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(sR + (uint32_t)(y * CC + cc) * 4));
+                    tot += t;
+                }
+                p.partial[((long long)(n0 + jj) * gridDim.x + tile) * p.Cexp + cbase + cc] = tot;
             }
-            p.partial[((long long)n * gridDim.x + tile) * p.Cexp + cbase + tid] = tot;
         }
         // E, the squeeze scratch and TMEM are reused only after the barrier at the top of the next chunk
     }
@@ -397,34 +418,45 @@ __global__ void __launch_bounds__(256, 2) k1_expand_dw_kernel(const K1Params p) 
     if (!NOEXP && warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)p.tmem_cols) : "memory");
 
-    // ---- SE excite by the last CTA of this crop (classic fence + ticket pattern; the sums stay in fixed order)
+    // ---- SE excite by the last CTA of this crop (classic fence + ticket pattern; the sums stay in fixed order; NB == 1 only)
     if (p.se_counter) {
         if (tid == 0) {
-            const int ticket = atomicAdd(p.se_counter + n, 1);
+            const int ticket = atomicAdd(p.se_counter + n0, 1);
             s_last = ticket == (int)(gridDim.x * gridDim.z) - 1;
-            if (s_last) p.se_counter[n] = 0;
+            if (s_last) p.se_counter[n0] = 0;
         }
         __syncthreads();
         if (s_last && !s_abort) {
             __threadfence();
             float* sm = reinterpret_cast<float*>(smem_raw + (sE - tc::smem_u32(smem_raw)));    // E is free now
-            se_gate_crop<true>(p.partial + (long long)n * gridDim.x * p.Cexp, (int)gridDim.x, 1.0f / (float)(p.Ho * p.Ho),
-                         p.w_se1t, p.b_se1, p.w_se2, p.b_se2, p.gate + (long long)n * p.Cexp, p.Cexp, p.Cse, sm);
+            se_gate_crop<true, NT>(p.partial + (long long)n0 * gridDim.x * p.Cexp, (int)gridDim.x, 1.0f / (float)(p.Ho * p.Ho),
+                         p.w_se1t, p.b_se1, p.w_se2, p.b_se2, p.gate + (long long)n0 * p.Cexp, p.Cexp, p.Cse, sm);
         }
     }
 }
 
-// Tile plan for one block: try a few tile shapes x chunk widths, prefer plans that let two CTAs share an SM
-// (<= 110 KB shared memory, <= 256 TMEM columns), then the most work per CTA.  Returns false when K1 cannot run it.
+// One tile plan: TH x TW output tile, R outputs per depthwise strip, CC expanded channels per chunk, NT threads per CTA,
+// NB crops per CTA.  Returns false when K1 cannot run it (shape does not divide, TMEM / shared memory exceeded).
 inline bool plan_k1_candidate(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, bool is_bf16, int TH, int TW, int R, int CC,
-                              K1Params* p, size_t* smem_out) {
-    if (Ho % TH || Ho % TW || Cexp % CC) return false;
+                              int NT, int NB, K1Params* p, size_t* smem_out) {
+    if (Ho % TH || Ho % TW || Cexp % CC || (NT != 256 && NT != 512) || NB < 1) return false;
     p->Hin = Hin; p->Ho = Ho; p->Cin = Cin; p->Cexp = Cexp; p->pad = pad;
     p->TH = TH; p->TW = TW;
     p->IH = (TH - 1) * s + k; p->IW = (TW - 1) * s + k;
     p->tiles_x = Ho / TW; p->tiles_y = Ho / TH;
-    p->mtiles = (p->IH * p->IW + BM - 1) / BM;
+    if (NB > 1 && p->tiles_x * p->tiles_y != 1) return false;
+    p->NB = NB;
+    // GEMM rows of a CTA = halo pixels inside the image; the largest count over all tiles sizes TMEM and the A buffer
+    int max_in = 0;
+    for (int ty = 0; ty < p->tiles_y; ++ty)
+        for (int tx = 0; tx < p->tiles_x; ++tx) {
+            const int iy0 = ty * TH * s - pad, ix0 = tx * TW * s - pad;
+            const int ih = std::min(p->IH, Hin - iy0) - std::max(0, -iy0), iw = std::min(p->IW, Hin - ix0) - std::max(0, -ix0);
+            max_in = std::max(max_in, ih * iw);
+        }
+    p->mtiles = (NB * max_in + BM - 1) / BM;
     if (p->mtiles > 3 || p->mtiles * CC > 512) return false;
+    p->rows_alloc = (NB * max_in + 7) & ~7;
     p->cpr = ((Cin >> 3) + 1 + 1) & ~1;
     p->nkb = (p->cpr + 7) / 8;
     p->CC = CC; p->n_chunks = Cexp / CC;
@@ -433,45 +465,73 @@ inline bool plan_k1_candidate(int Hin, int Ho, int Cin, int Cexp, int k, int s, 
     while (cols < p->mtiles * CC) cols <<= 1;
     p->tmem_cols = cols;
     p->pitchE = CC * 2 + 16;
-    p->PY = 256 / (CC / 4);
-    if (p->PY < 1) return false;
+    p->PYc = NT / (CC / 4) / NB;
+    p->PY = p->PYc * NB;
+    if (p->PYc < 1 || NB * CC > NT) return false;
     const int spr = (TW + R - 1) / R;         // a ragged last strip computes (and discards) up to R-1 extra outputs
     p->spr_log2 = spr == 1 ? 0 : spr == 2 ? 1 : spr == 4 ? 2 : -1;
     if (p->spr_log2 < 0) return false;
     p->idesc = tc::make_idesc(is_bf16, CC);
-    p->smem_A = p->nkb * p->mtiles * BM * 128;
-    p->smem_W = ((p->nkb * CC * 128) + 1023) & ~1023;
-    p->smem_C = (((k * k + 1) * CC * 4) + 1023) & ~1023;
+    p->smem_A = p->nkb * p->rows_alloc * 128;           // multiple of 1024 (rows_alloc % 8 == 0)
+    p->smem_W = p->nkb * CC * 128;                      // multiple of 2048 (CC % 16 == 0)
+    p->smem_C = (k * k + 1) * CC * 4;
     // slack rows: a ragged strip still LOADS the columns of its discarded outputs
-    p->smem_E = (((p->IH * p->IW + R * s + 16) * p->pitchE) + 1023) & ~1023;
+    p->e_rows = p->IH * p->IW + R * s + 16;
+    p->smem_E = NB * p->e_rows * p->pitchE;
     *smem_out = (size_t)p->smem_A + 2 * p->smem_W + 2 * p->smem_C + p->smem_E + (size_t)p->PY * CC * 4 + 1024;
-    return *smem_out <= 200 * 1024;
+    // the UMMA of the last M tile reads 128 rows even when fewer are staged: that read must stay inside the CTA's window
+    if ((size_t)(p->nkb - 1) * p->rows_alloc * 128 + (size_t)p->mtiles * BM * 128 + 1024 > *smem_out) return false;
+    return *smem_out <= 225 * 1024;
 }
 
-inline bool plan_k1(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, bool is_bf16, K1Params* p, int* R_out, size_t* smem_out) {
+// can two CTAs of this plan share an SM?  (228 KB per SM, 1 KB reserved per CTA, 512 TMEM columns)
+inline bool k1_two_per_sm(const K1Params& p, size_t smem, int NT) { return NT == 256 && smem <= 115000 && p.tmem_cols <= 256; }
+
+struct K1Choice { int th, tw, r, cc, nt, nb; };
+
+// Per-block plan.  The table holds the plans measured fastest on B200 by tools/tune_k1.py; blocks without an entry
+// (or whose entry does not fit) fall back to a small search ranked by a thread-instruction model.
+inline bool plan_k1(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, bool is_bf16, bool allow_nb, K1Params* p, K1Choice* choice,
+                    size_t* smem_out) {
+    struct Tuned { int hin, k, s, cexp; K1Choice c; };
+    static const Tuned tuned[] = {
+        {112, 3, 2, 96, {8, 8, 4, 48, 256, 1}},      // block 2
+        {56, 3, 1, 144, {14, 14, 7, 48, 256, 1}},    // block 3
+        {56, 5, 2, 144, {7, 7, 4, 48, 256, 1}},      // block 4
+        {28, 5, 1, 240, {14, 14, 7, 48, 256, 1}},    // block 5
+        {28, 3, 2, 240, {7, 7, 4, 80, 256, 1}},      // block 6
+        {14, 3, 1, 480, {14, 14, 7, 96, 256, 1}},    // blocks 7, 8
+        {14, 5, 1, 480, {14, 14, 7, 96, 512, 1}},    // block 9
+        {14, 5, 1, 672, {14, 14, 7, 112, 512, 1}},   // blocks 10, 11
+        {14, 5, 2, 672, {7, 7, 7, 112, 512, 1}},     // block 12
+        {7, 5, 1, 1152, {7, 7, 4, 64, 512, 2}},      // blocks 13-15
+        {7, 3, 1, 1152, {7, 7, 7, 96, 256, 2}},      // block 16
+        {7, 5, 1, 1152, {7, 7, 4, 64, 256, 1}},      // blocks 13-15 when a CTA may hold one crop only (fused SE tail)
+        {7, 3, 1, 1152, {7, 7, 7, 96, 256, 1}},      // block 16, ditto
+    };
+    for (const Tuned& t : tuned)
+        if (t.hin == Hin && t.k == k && t.s == s && t.cexp == Cexp && (allow_nb || t.c.nb == 1)) {
+            K1Params q{};
+            size_t smem = 0;
+            if (plan_k1_candidate(Hin, Ho, Cin, Cexp, k, s, pad, is_bf16, t.c.th, t.c.tw, t.c.r, t.c.cc, t.c.nt, t.c.nb, &q, &smem)) {
+                *p = q; *choice = t.c; *smem_out = smem;
+                return true;
+            }
+        }
     struct Cand { int th, tw, r; };
     const Cand s1[] = {{14, 14, 7}, {7, 14, 7}, {7, 7, 7}, {7, 7, 4}};
     const Cand s2k3[] = {{8, 8, 4}, {7, 7, 7}, {7, 7, 4}};
     const Cand s2[] = {{7, 7, 7}, {7, 7, 4}};
     const Cand* cands = s == 1 ? s1 : (k == 3 ? s2k3 : s2);
     const int ncand = s == 1 ? 4 : (k == 3 ? 3 : 2);
-    // plans measured fastest on B200 by tools/tune_k1.py (round 1) where they differ from the model's pick
-    if (s == 1 && k == 5 && (Hin == 28 || Hin == 14) && Cexp % 48 == 0) {
-        K1Params q{};
-        size_t smem = 0;
-        if (plan_k1_candidate(Hin, Ho, Cin, Cexp, k, s, pad, is_bf16, 14, 14, 7, 48, &q, &smem)) {
-            *p = q; *R_out = 7; *smem_out = smem;
-            return true;
-        }
-    }
     bool found = false;
     double best = -1;
     for (int i = 0; i < ncand; ++i)
         for (int cc = 128; cc >= 16; cc -= 16) {
             K1Params q{};
             size_t smem = 0;
-            if (!plan_k1_candidate(Hin, Ho, Cin, Cexp, k, s, pad, is_bf16, cands[i].th, cands[i].tw, cands[i].r, cc, &q, &smem)) continue;
-            const bool two = smem <= 110 * 1024 && q.tmem_cols <= 256;
+            if (!plan_k1_candidate(Hin, Ho, Cin, Cexp, k, s, pad, is_bf16, cands[i].th, cands[i].tw, cands[i].r, cc, 256, 1, &q, &smem)) continue;
+            const bool two = k1_two_per_sm(q, smem, 256);
             // rough thread-instruction model of one CTA (constants from the ncu source view of round 1):
             //   A fill ~20 / (pixel, chunk); per chunk: epilogue-1 ~4 / E element, depthwise ~1.8 x FMA count over
             //   whole rounds of the 256 threads, ~400 / thread of barrier + prefetch overhead
@@ -479,12 +539,14 @@ inline bool plan_k1(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, b
             const double items = (double)(th * ((tw + R - 1) / R)) * (cc / 4);
             const double lanes = (double)q.PY * (cc / 4);
             const double rounds = (double)(long long)((items + lanes - 1) / lanes);
-            const double epi = (double)q.IH * q.IW * cc * 4.0;
+            const double epi = (double)q.mtiles * BM * cc * 4.0;
             const double dw = rounds * 256.0 * R * k * k * 4 * 1.8;
-            const double per_cta = (double)q.IH * q.IW * (Cin / 8) * 20.0 + q.n_chunks * (epi + dw + 256.0 * 400.0);
+            const double per_cta = (double)q.rows_alloc * (Cin / 8) * 20.0 + q.n_chunks * (epi + dw + 256.0 * 400.0);
             double cost = per_cta / ((double)th * tw * Cexp);
             if (!two) cost *= 1.4;
-            if (best < 0 || cost < best) { best = cost; *p = q; *R_out = R; *smem_out = smem; found = true; }
+            if (best < 0 || cost < best) {
+                best = cost; *p = q; *choice = K1Choice{th, tw, R, cc, 256, 1}; *smem_out = smem; found = true;
+            }
         }
     return found;
 }
@@ -496,35 +558,48 @@ inline bool plan_dw_only(int Hin, int C, int k, int s, int pad, K1Params* p, siz
     p->Hin = Hin; p->Ho = Hin; p->Cin = C; p->Cexp = C; p->pad = pad;
     p->TH = 14; p->TW = 14; p->IH = 16; p->IW = 16;
     p->tiles_x = Hin / 14; p->tiles_y = Hin / 14;
-    p->mtiles = 2; p->cpr = 2; p->nkb = 1; p->CC = C; p->n_chunks = 1; p->tmem_cols = 32;
+    p->mtiles = 2; p->rows_alloc = 256; p->cpr = 2; p->nkb = 1; p->CC = C; p->n_chunks = 1; p->tmem_cols = 32;
+    p->NB = 1;
     p->pitchE = C * 2 + 16;
     p->PY = 256 / (C / 4);
+    p->PYc = p->PY;
     p->spr_log2 = 1;
     p->smem_A = 0; p->smem_W = 0; p->chunks_per_cta = 1;
     p->smem_C = (((k * k + 1) * C * 4) + 1023) & ~1023;
-    p->smem_E = (((16 * 16 + 7 + 16) * p->pitchE) + 1023) & ~1023;
+    p->e_rows = 16 * 16 + 7 + 16;
+    p->smem_E = ((p->e_rows * p->pitchE) + 1023) & ~1023;
     *smem_out = (size_t)2 * p->smem_C + p->smem_E + (size_t)p->PY * C * 4 + 1024;
     return true;
 }
 
 template <typename T>
-int launch_dw_only(cudaStream_t stream, const K1Params& p, size_t smem, int n_crops) {
+int launch_dw_only(cudaStream_t stream, K1Params p, size_t smem, int n_crops) {
+    p.N = n_crops;
     dim3 grid(p.tiles_x * p.tiles_y, n_crops, 1);
     auto kfn = k1_expand_dw_kernel<T, 3, 1, 7, true>;
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024) != cudaSuccess) return -1;
     kfn<<<grid, 256, smem, stream>>>(p);
     return 0;
 }
 
+inline bool k1_has_instance(int k, int s, int R) { return (k == 3 || k == 5) && (s == 1 || s == 2) && (R == 4 || R == 7); }
+
 template <typename T>
-int launch_k1(cudaStream_t stream, const K1Params& p, int k, int s, int R, size_t smem, int n_crops) {
-    dim3 grid(p.tiles_x * p.tiles_y, n_crops, (p.n_chunks + p.chunks_per_cta - 1) / p.chunks_per_cta);
-#define K1(KS, S, RR)                                                                                            \
-    do {                                                                                                         \
-        auto kfn = p.CC == 48 ? k1_expand_dw_kernel<T, KS, S, RR, false, 48> : k1_expand_dw_kernel<T, KS, S, RR>;  \
-        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1; \
-        kfn<<<grid, 256, smem, stream>>>(p);                                                                     \
-        return 0;                                                                                                \
+int launch_k1(cudaStream_t stream, K1Params p, int k, int s, int R, int NT, size_t smem, int n_crops) {
+    p.N = n_crops;
+    dim3 grid(p.tiles_x * p.tiles_y, (n_crops + p.NB - 1) / p.NB, (p.n_chunks + p.chunks_per_cta - 1) / p.chunks_per_cta);
+#define K1_GO(KFN)                                                                                                         \
+    do {                                                                                                                   \
+        auto kfn = KFN;                                                                                                    \
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024) != cudaSuccess) return -1;  \
+        kfn<<<grid, NT, smem, stream>>>(p);                                                                                \
+        return 0;                                                                                                          \
+    } while (0)
+#define K1(KS, S, RR)                                                                      \
+    do {                                                                                   \
+        if (NT == 512) K1_GO((k1_expand_dw_kernel<T, KS, S, RR, false, 0, 512>));          \
+        if (p.CC == 48) K1_GO((k1_expand_dw_kernel<T, KS, S, RR, false, 48, 256>));        \
+        K1_GO((k1_expand_dw_kernel<T, KS, S, RR, false, 0, 256>));                         \
     } while (0)
     if (k == 3 && s == 2 && R == 4) K1(3, 2, 4);
     if (k == 3 && s == 1 && R == 7) K1(3, 1, 7);
@@ -535,6 +610,7 @@ int launch_k1(cudaStream_t stream, const K1Params& p, int k, int s, int R, size_
     if (k == 5 && s == 1 && R == 4) K1(5, 1, 4);
     if (k == 5 && s == 2 && R == 4) K1(5, 2, 4);
 #undef K1
+#undef K1_GO
     return 1;
 }
 

@@ -90,7 +90,7 @@ struct BlockW {   // device pointers into the fp32 arena
     float *w_dw_h = nullptr, *b_dw_h = nullptr;   // 0.5 * depthwise weights / shift (K1)
 };
 
-struct K1Plan { bool valid = false; whenet::fused::K1Params p{}; int R = 0; size_t smem = 0; };
+struct K1Plan { bool valid = false; whenet::fused::K1Params p{}; int R = 0; int NT = 256; size_t smem = 0; };
 struct K1TPlan { bool valid = false; whenet::fused::K1TParams p{}; size_t smem = 0; };
 struct GraphKey {
     int n, in_u8, sig;
@@ -396,13 +396,15 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
         const T* dw_in = cur;
         int tiles = 0;
         bool did_k1 = false;
-        if (i == 0 && did_k0) { did_k1 = true; tiles = 64; }      // K0 already produced D, the partials and the gate
+        bool se_in_k1 = false;      // the SE gate came out of the fused kernel's tail (option se_fused)
+        if (i == 0 && did_k0) { did_k1 = true; se_in_k1 = c->se_fused != 0; tiles = 64; }      // K0 already produced D, the partials and the gate
         if constexpr (sizeof(T) == 2) {
             if (i == 0 && !did_k1 && c->use_fused && c->dw1_fused && c->dw1.valid) {
                 whenet::fused::K1Params p = c->dw1.p;
                 p.in = cur; p.wt_aug = nullptr; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial;
                 p.w_se1t = w.w_se1t; p.b_se1 = w.b_se1; p.w_se2 = w.w_se2; p.b_se2 = w.b_se2; p.gate = c->d_gate; p.Cse = b.cse;
-                p.se_counter = c->se_fused ? c->d_se_counter : nullptr;
+                se_in_k1 = c->se_fused != 0;
+                p.se_counter = se_in_k1 ? c->d_se_counter : nullptr;
                 snprintf(nm, sizeof nm, "b%02d.dw", b.idx);
                 Scope sc(c, nm, (double)nb * 2.0 * b.hin * b.hin * b.cexp * sizeof(T), 2.0 * nb * (double)b.hout * b.hout * b.k * b.k * b.cexp);
                 int rc = whenet::fused::launch_dw_only<T>(c->stream, p, c->dw1.smem, nb);
@@ -426,10 +428,11 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
                 whenet::fused::K1Params p = c->k1[i].p;
                 p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial;
                 p.w_se1t = w.w_se1t; p.b_se1 = w.b_se1; p.w_se2 = w.w_se2; p.b_se2 = w.b_se2; p.gate = c->d_gate; p.Cse = b.cse;
-                p.se_counter = c->se_fused ? c->d_se_counter : nullptr;
+                se_in_k1 = c->se_fused && p.NB == 1;
+                p.se_counter = se_in_k1 ? c->d_se_counter : nullptr;
                 // small batches: spread one crop's chunks over several CTAs until the grid covers the SMs about twice
                 {
-                    const long long ctas = (long long)p.tiles_x * p.tiles_y * nb;
+                    const long long ctas = (long long)p.tiles_x * p.tiles_y * ((nb + p.NB - 1) / p.NB);
                     int split = 1;
                     while (split < p.n_chunks && ctas * split < 296) ++split;
                     p.chunks_per_cta = (p.n_chunks + split - 1) / split;
@@ -437,7 +440,7 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
                 snprintf(nm, sizeof nm, "b%02d.k1", b.idx);
                 Scope sc(c, nm, (double)nb * ((double)b.hin * b.hin * b.cin + (double)b.hout * b.hout * b.cexp) * sizeof(T),
                          2.0 * nb * ((double)b.hin * b.hin * b.cin * b.cexp + (double)b.hout * b.hout * b.k * b.k * b.cexp));
-                int rc = whenet::fused::launch_k1<T>(c->stream, p, b.k, b.s, c->k1[i].R, c->k1[i].smem, nb);
+                int rc = whenet::fused::launch_k1<T>(c->stream, p, b.k, b.s, c->k1[i].R, c->k1[i].NT, c->k1[i].smem, nb);
                 if (rc != 0) return fail(WHENET_ECUDA, "K1 launch failed for block %d (rc=%d)", b.idx, rc);
                 CK(cudaGetLastError());
                 c->tc_used = true;
@@ -458,7 +461,7 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
         if (rc) return rc;
         }
         int rc = 0;
-        if (!(did_k1 && c->se_fused && c->k1_variant == 1)) {
+        if (!se_in_k1) {
             snprintf(nm, sizeof nm, "b%02d.se", b.idx);
             Scope sc(c, nm, (double)nb * (tiles + 1) * b.cexp * 4.0, 4.0 * nb * b.cexp * b.cse);
             const float inv_hw = 1.0f / (float)(b.hout * b.hout);
@@ -737,8 +740,11 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
             const BlockCfg& b = c->blocks[i];
             if (!b.has_expand) continue;
             K1Plan& pl = c->k1[i];
-            pl.valid = whenet::fused::plan_k1(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, precision == WHENET_PRECISION_BF16,
-                                              &pl.p, &pl.R, &pl.smem);
+            whenet::fused::K1Choice ch{};
+            pl.valid = whenet::fused::plan_k1(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, precision == WHENET_PRECISION_BF16, true,
+                                              &pl.p, &ch, &pl.smem);
+            pl.R = ch.r;
+            pl.NT = ch.nt;
             K1TPlan& pt = c->k1t[i];
             pt.valid = whenet::fused::plan_k1t(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, precision == WHENET_PRECISION_BF16,
                                                &pt.p, &pt.smem);
@@ -1115,20 +1121,20 @@ int whenet_debug_conv1x1(whenet_ctx* c, int use_tc, const float* A, const float*
     return fail(WHENET_EINVAL, "bad precision");
 }
 
-int whenet_debug_set_k1_plan(whenet_ctx* c, int block, int th, int tw, int r, int cc) {
+int whenet_debug_set_k1_plan(whenet_ctx* c, int block, int th, int tw, int r, int cc, int nt, int nb) {
     if (!c || block < 2 || block > (int)c->blocks.size()) return fail(WHENET_EINVAL, "bad block index");
     if (c->precision == WHENET_PRECISION_FP32) return fail(WHENET_EINVAL, "K1 needs a 16-bit storage mode");
     const BlockCfg& b = c->blocks[block - 1];
-    if (cc < 16 || cc > 128 || (cc & 15) || r < 1 || th < 1 || tw < 1) return fail(WHENET_EINVAL, "bad plan parameters");
-    if (!((b.k == 3 && b.s == 2 && (r == 4 || r == 7)) || (b.k == 3 && b.s == 1 && (r == 7 || r == 4)) ||
-          (b.k == 5 && b.s == 1 && (r == 7 || r == 4)) || (b.k == 5 && b.s == 2 && (r == 7 || r == 4))))
-        return fail(WHENET_EINVAL, "no K1 instantiation for k=%d s=%d r=%d", b.k, b.s, r);
+    if (cc < 16 || cc > 128 || (cc & 15) || r < 1 || th < 1 || tw < 1 || (nt != 256 && nt != 512) || nb < 1 || nb > 2)
+        return fail(WHENET_EINVAL, "bad plan parameters");
+    if (!whenet::fused::k1_has_instance(b.k, b.s, r)) return fail(WHENET_EINVAL, "no K1 instantiation for k=%d s=%d r=%d", b.k, b.s, r);
     K1Plan pl;
     if (!whenet::fused::plan_k1_candidate(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, c->precision == WHENET_PRECISION_BF16,
-                                          th, tw, r, cc, &pl.p, &pl.smem))
-        return fail(WHENET_EINVAL, "plan %dx%d r%d cc%d does not fit block %d", th, tw, r, cc, block);
+                                          th, tw, r, cc, nt, nb, &pl.p, &pl.smem))
+        return fail(WHENET_EINVAL, "plan %dx%d r%d cc%d nt%d nb%d does not fit block %d", th, tw, r, cc, nt, nb, block);
     pl.valid = true;
     pl.R = r;
+    pl.NT = nt;
     c->k1[block - 1] = pl;
     free_ws(c);      // the squeeze-partials buffer depends on the tile count
     return 0;

@@ -245,9 +245,9 @@ class WHENet:
                                            _ptr(out), M, K, N, int(hw or M), int(swish)))
         return out
 
-    def set_k1_plan(self, block: int, th: int, tw: int, r: int, cc: int) -> bool:
+    def set_k1_plan(self, block: int, th: int, tw: int, r: int, cc: int, nt: int = 256, nb: int = 1) -> bool:
         """Tuning hook (see whenet_debug_set_k1_plan); returns False when the plan cannot run."""
-        return self._L.whenet_debug_set_k1_plan(self._h, block, th, tw, r, cc) == 0
+        return self._L.whenet_debug_set_k1_plan(self._h, block, th, tw, r, cc, nt, nb) == 0
 
     def enable_profile(self, on: bool = True):
         check(self._L.whenet_profile_enable(self._h, int(on)))

@@ -135,8 +135,9 @@ int whenet_debug_conv1x1(whenet_ctx* ctx, int use_tc, const float* A, const floa
                          int64_t M, int K, int N, int hw, int swish);
 
 /* Tuning hook: force the K1 (fused expand+depthwise) tile plan of block `block` (2..16): output tile
- * th x tw, strips of r outputs, cc expanded channels per chunk.  WHENET_EINVAL if the plan cannot run. */
-int whenet_debug_set_k1_plan(whenet_ctx* ctx, int block, int th, int tw, int r, int cc);
+ * th x tw, strips of r outputs, cc expanded channels per chunk, nt threads per CTA (256 or 512), nb crops
+ * per CTA (2 only where one tile is the whole image).  WHENET_EINVAL if the plan cannot run. */
+int whenet_debug_set_k1_plan(whenet_ctx* ctx, int block, int th, int tw, int r, int cc, int nt, int nb);
 
 /* Time every kernel of the NEXT forwards with CUDA events. */
 int whenet_profile_enable(whenet_ctx* ctx, int enable);

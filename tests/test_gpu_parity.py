@@ -177,6 +177,52 @@ def test_fused_k1t_tensor_core_depthwise(prec, oracle32, sample_crops):
     m.close()
 
 
+K1_PLAN_SETS = {
+    # 512-thread CTAs (one per SM) on the late blocks
+    "nt512": {7: (14, 14, 7, 96, 512, 1), 8: (14, 14, 7, 96, 512, 1), 9: (14, 14, 7, 96, 512, 1), 10: (14, 14, 7, 96, 512, 1),
+              11: (14, 14, 7, 112, 512, 1), 12: (7, 7, 4, 96, 512, 1), 13: (7, 7, 4, 96, 512, 1), 14: (7, 7, 4, 64, 512, 1),
+              15: (7, 7, 7, 96, 512, 1), 16: (7, 7, 4, 96, 512, 1)},
+    # two crops per CTA on the 7x7 stages; small two-per-SM plans elsewhere (edge tiles with fewer GEMM rows than interior ones)
+    "nb2": {2: (8, 7, 4, 48, 256, 1), 3: (7, 7, 4, 48, 256, 1), 5: (7, 7, 4, 48, 256, 1), 9: (14, 14, 7, 32, 256, 1),
+            10: (7, 7, 4, 48, 256, 1), 12: (7, 7, 4, 32, 256, 1), 13: (7, 7, 4, 64, 512, 2), 14: (7, 7, 7, 64, 512, 2),
+            15: (7, 7, 4, 48, 512, 2), 16: (7, 7, 7, 64, 512, 2)},
+    "nb2_nt256": {13: (7, 7, 4, 64, 256, 2), 14: (7, 7, 4, 48, 256, 2), 16: (7, 7, 4, 64, 256, 2), 6: (7, 7, 4, 48, 256, 1),
+                  4: (7, 7, 7, 48, 256, 1)},
+}
+
+
+@pytest.mark.parametrize("plan_set", sorted(K1_PLAN_SETS))
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_fused_k1_plan_variants(prec, plan_set, oracle32, sample_crops, jitter_crops):
+    """Every K1 tile-plan family (512-thread CTAs, two crops per CTA, small edge-tile plans) against the oracle taps on an
+    odd crop count (the last two-crop CTA is half empty), and bitwise batch invariance under those plans."""
+    import whenet_b200
+    crops = np.concatenate([sample_crops, jitter_crops[:1]])
+    m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=8)
+    for blk, plan in K1_PLAN_SETS[plan_set].items():
+        assert m.set_k1_plan(blk, *plan), (blk, plan)
+    taps = {}
+    ref_ang = np.stack(oracle32.get_angle(crops, taps), axis=1)
+    m.enable_taps(True)
+    got = np.stack(m.get_angle(crops), axis=1)
+    lim = 0.12 if prec == "bf16" else 0.02
+    for i in range(1, 17):
+        for kind in ("dw", "gate", "block"):
+            nm = "%s%d" % (kind, i)
+            ref = taps[nm].astype(np.float64).reshape(-1)
+            g = m.tap(nm).astype(np.float64)
+            e = float(np.sqrt(((g - ref) ** 2).mean()) / (np.sqrt((ref ** 2).mean()) + 1e-30))
+            assert e < lim, (plan_set, nm, e)
+    assert np.abs(got - ref_ang).max() < (1.5 if prec == "bf16" else 0.15)
+    m.enable_taps(False)
+    for i in range(3):
+        one = np.stack(m.get_angle(crops[i:i + 1]), axis=1)
+        assert np.array_equal(one[0], got[i]), (plan_set, i)
+    pair = np.stack(m.get_angle(crops[1:3]), axis=1)
+    assert np.array_equal(pair, got[1:3])
+    m.close()
+
+
 def test_fused_k1_batch_invariance(sample_crops, jitter_crops):
     import whenet_b200
     crops = np.concatenate([sample_crops, jitter_crops] * 3)[:19]
