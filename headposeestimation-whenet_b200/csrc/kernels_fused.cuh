@@ -33,6 +33,8 @@ namespace fused {
 using tc::BK;
 using tc::BM;
 
+constexpr size_t K1_MAX_SMEM = 227 * 1024 - 256;     // opt-in limit per CTA minus the kernel's static shared memory
+
 struct K1Params {
     const void* in;        // T [N][Hin][Hin][Cin]
     // every K1 constant is pre-multiplied by 1/2 (exact): swish(x) = h + h*tanh(h) with h = x/2 then needs no multiply
@@ -45,6 +47,11 @@ struct K1Params {
     const float *w_se1t, *b_se1, *w_se2, *b_se2;
     float* gate;           // [N][Cexp]
     int* se_counter;       // [N], zero on entry, self-resetting
+    int se_tail;           // 1: this CTA holds every pixel and channel of its crops (one tile per image, no chunk split): it
+                           // keeps the channel means in shared memory and computes the gate itself - no ticket, no fence
+    float inv_hw;          // 1 / (Ho*Ho), as the stand-alone SE kernel gets it
+    int scale_out;         // se_tail only: multiply the depthwise output by the gate in place (16-bit rounding of d*g, exactly
+                           // what the project conv's gate pass would feed the tensor core), so the project runs ungated
     int Cse;
     int Hin, Ho, Cin, Cexp, pad;
     int TH, TW, IH, IW;    // output tile, input halo tile
@@ -110,7 +117,7 @@ __device__ __forceinline__ uint32_t sw128(int r, int c) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
-// exact floor(x / d) for the small non-negative ints of the tile arithmetic (x < 2^14), with inv = 1.0f / d:
+// exact floor(x / d) for the small non-negative ints of the tile arithmetic (x < 2^17, d < 2^8), with inv = 1.0f / d:
 // (x + 0.5) / d is at least 0.5 / d away from every integer, far more than the float rounding error
 __device__ __forceinline__ int div_small(int x, float inv) { return __float2int_rz(((float)x + 0.5f) * inv); }
 
@@ -138,6 +145,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(con
     const uint32_t sC = sW + 2 * p.smem_W;                      // 2 x { b_dw[CC], w_dw[KS*KS][CC] } fp32
     const uint32_t sE = sC + 2 * p.smem_C;                      // [NB][e_rows][pitchE]
     const uint32_t sR = sE + p.smem_E;                          // [PY][CC] fp32 squeeze partials
+    float* const sM = reinterpret_cast<float*>(smem_raw + (sR + (uint32_t)(p.PY * CC) * 4u - tc::smem_u32(smem_raw)));
+                                                                // [NB][Cexp] channel means, [Cse] hidden (se_tail only)
 
     const T* in = reinterpret_cast<const T*>(p.in);
     const T* wt = reinterpret_cast<const T*>(p.wt_aug);
@@ -159,6 +168,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(con
     const int kchunks = p.Cin >> 3;                     // data chunks per row; chunk `kchunks` holds the ones / the shift
     const int Kaug = p.Cin + 8;
     const uint32_t a_kb_stride = (uint32_t)p.rows_alloc * 128u;
+    const float inv_cpr = 1.0f / (float)p.cpr, inv_q = 4.0f / (float)CC;
 
     if (tid == 0) {
         tc::mbar_init(&mbar, 1);
@@ -212,7 +222,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(con
         const uint32_t w_dst = sW + buf * p.smem_W;
         const int per_row = p.cpr;                                 // data chunks + shift chunk (+ zero pad chunk)
         for (int idx = tid; idx < (NOEXP ? 0 : CC * per_row); idx += NT) {
-            const int r = idx / per_row, c = idx - r * per_row;
+            const int r = div_small(idx, inv_cpr), c = idx - r * per_row;
             const bool valid = c <= kchunks;
             cp_async16(w_dst + (uint32_t)(c >> 3) * CC * 128 + sw128(r, c & 7),
                        valid ? wt + (long long)(cbase + r) * Kaug + c * 8 : wt, valid);
@@ -223,7 +233,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(con
         const uint32_t c_dst = sC + buf * p.smem_C;
         const int q = CC >> 2;                                   // 16-byte pieces per constant row
         for (int idx = tid; idx < (KS * KS + 1) * q; idx += NT) {
-            const int row = idx / q, j = idx - row * q;
+            const int row = div_small(idx, inv_q), j = idx - row * q;
             const float* src = row == 0 ? p.b_dw + cbase + j * 4 : p.w_dw + (long long)(row - 1) * p.Cexp + cbase + j * 4;
             cp_async16(c_dst + (uint32_t)(row * CC + j * 4) * 4, src, true);
         }
@@ -400,13 +410,27 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(con
         if (ok && tid < p.NB * CC) {
             const int jj = tid / CC, cc = tid - jj * CC;
             if (jj < nb_here) {
-                float tot = 0.f;
-                for (int y = jj * p.PYc; y < (jj + 1) * p.PYc; ++y) {
-                    float t;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(sR + (uint32_t)(y * CC + cc) * 4));
-                    tot += t;
+                // four independent chains (lane mod 4) keep this short: the two warps doing it are the ones every other warp
+                // waits for at the next barrier.  Fixed association order -> reproducible bits.
+                float s4[4] = {0.f, 0.f, 0.f, 0.f};
+                const uint32_t r0 = sR + (uint32_t)(jj * p.PYc * CC + cc) * 4;
+                int y = 0;
+                for (; y + 3 < p.PYc; y += 4) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float t;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(r0 + (uint32_t)((y + i) * CC) * 4));
+                        s4[i] += t;
+                    }
                 }
+                for (; y < p.PYc; ++y) {
+                    float t;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(r0 + (uint32_t)(y * CC) * 4));
+                    s4[y & 3] += t;
+                }
+                const float tot = (s4[0] + s4[1]) + (s4[2] + s4[3]);
                 p.partial[((long long)(n0 + jj) * gridDim.x + tile) * p.Cexp + cbase + cc] = tot;
+                if (p.se_tail) sM[jj * p.Cexp + cbase + cc] = tot * p.inv_hw;      // == the mean se_gate_crop forms from one tile
             }
         }
         // E, the squeeze scratch and TMEM are reused only after the barrier at the top of the next chunk
@@ -418,6 +442,26 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(con
     if (!NOEXP && warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)p.tmem_cols) : "memory");
 
+    // ---- SE excite for the crops of this CTA when it holds all of their pixels and channels
+    if (p.se_tail && !s_abort) {
+        for (int jj = 0; jj < nb_here; ++jj) {
+            float* const g_sm = sM + jj * p.Cexp;           // means in, gate out
+            se_gate_fc<NT>(g_sm, sM + p.NB * p.Cexp, p.w_se1t, p.b_se1, p.w_se2, p.b_se2,
+                           p.gate + (long long)(n0 + jj) * p.Cexp, p.Cexp, p.Cse, g_sm);
+            __syncthreads();
+            if (p.scale_out) {
+                // D of this crop was written by this CTA (visible after the barriers above) and is still in L2
+                T* const d_n = out + (long long)(n0 + jj) * p.Ho * p.Ho * p.Cexp;
+                const int cv8 = p.Cexp >> 3, total = p.Ho * p.Ho * cv8;
+                const float inv_cv8 = 1.0f / (float)cv8;
+                for (int v = tid; v < total; v += NT) {
+                    const int c8 = (v - div_small(v, inv_cv8) * cv8) * 8;
+                    uint4* ptr = reinterpret_cast<uint4*>(d_n) + v;
+                    *ptr = tc::scale8s<T>(__ldcg(ptr), tc::smem_u32(g_sm + c8));
+                }
+            }
+        }
+    }
     // ---- SE excite by the last CTA of this crop (classic fence + ticket pattern; the sums stay in fixed order; NB == 1 only)
     if (p.se_counter) {
         if (tid == 0) {
@@ -478,10 +522,11 @@ inline bool plan_k1_candidate(int Hin, int Ho, int Cin, int Cexp, int k, int s, 
     // slack rows: a ragged strip still LOADS the columns of its discarded outputs
     p->e_rows = p->IH * p->IW + R * s + 16;
     p->smem_E = NB * p->e_rows * p->pitchE;
-    *smem_out = (size_t)p->smem_A + 2 * p->smem_W + 2 * p->smem_C + p->smem_E + (size_t)p->PY * CC * 4 + 1024;
+    const size_t se_tail_bytes = p->tiles_x * p->tiles_y == 1 ? (size_t)(NB * Cexp + 64) * 4 : 0;     // means + hidden layer
+    *smem_out = (size_t)p->smem_A + 2 * p->smem_W + 2 * p->smem_C + p->smem_E + (size_t)p->PY * CC * 4 + se_tail_bytes + 1024;
     // the UMMA of the last M tile reads 128 rows even when fewer are staged: that read must stay inside the CTA's window
     if ((size_t)(p->nkb - 1) * p->rows_alloc * 128 + (size_t)p->mtiles * BM * 128 + 1024 > *smem_out) return false;
-    return *smem_out <= 225 * 1024;
+    return *smem_out <= K1_MAX_SMEM;
 }
 
 // can two CTAs of this plan share an SM?  (228 KB per SM, 1 KB reserved per CTA, 512 TMEM columns)
@@ -499,13 +544,13 @@ inline bool plan_k1(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, b
         {56, 3, 1, 144, {14, 14, 7, 48, 256, 1}},    // block 3
         {56, 5, 2, 144, {7, 7, 4, 48, 256, 1}},      // block 4
         {28, 5, 1, 240, {14, 14, 7, 48, 256, 1}},    // block 5
-        {28, 3, 2, 240, {7, 7, 4, 80, 256, 1}},      // block 6
-        {14, 3, 1, 480, {14, 14, 7, 96, 256, 1}},    // blocks 7, 8
+        {28, 3, 2, 240, {7, 7, 7, 80, 256, 1}},      // block 6
+        {14, 3, 1, 480, {14, 14, 7, 96, 512, 1}},    // blocks 7, 8
         {14, 5, 1, 480, {14, 14, 7, 96, 512, 1}},    // block 9
         {14, 5, 1, 672, {14, 14, 7, 112, 512, 1}},   // blocks 10, 11
         {14, 5, 2, 672, {7, 7, 7, 112, 512, 1}},     // block 12
-        {7, 5, 1, 1152, {7, 7, 4, 64, 512, 2}},      // blocks 13-15
-        {7, 3, 1, 1152, {7, 7, 7, 96, 256, 2}},      // block 16
+        {7, 5, 1, 1152, {7, 7, 7, 64, 512, 2}},      // blocks 13-15
+        {7, 3, 1, 1152, {7, 7, 7, 96, 512, 2}},      // block 16
         {7, 5, 1, 1152, {7, 7, 4, 64, 256, 1}},      // blocks 13-15 when a CTA may hold one crop only (fused SE tail)
         {7, 3, 1, 1152, {7, 7, 7, 96, 256, 1}},      // block 16, ditto
     };
@@ -577,7 +622,7 @@ int launch_dw_only(cudaStream_t stream, K1Params p, size_t smem, int n_crops) {
     p.N = n_crops;
     dim3 grid(p.tiles_x * p.tiles_y, n_crops, 1);
     auto kfn = k1_expand_dw_kernel<T, 3, 1, 7, true>;
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_MAX_SMEM) != cudaSuccess) return -1;
     kfn<<<grid, 256, smem, stream>>>(p);
     return 0;
 }
@@ -591,7 +636,7 @@ int launch_k1(cudaStream_t stream, K1Params p, int k, int s, int R, int NT, size
 #define K1_GO(KFN)                                                                                                         \
     do {                                                                                                                   \
         auto kfn = KFN;                                                                                                    \
-        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024) != cudaSuccess) return -1;  \
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_MAX_SMEM) != cudaSuccess) return -1;  \
         kfn<<<grid, NT, smem, stream>>>(p);                                                                                \
         return 0;                                                                                                          \
     } while (0)

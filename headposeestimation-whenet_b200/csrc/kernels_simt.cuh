@@ -498,6 +498,32 @@ __global__ void __launch_bounds__(256) dw_strip_kernel(const T* __restrict__ in,
 // Device function for ONE crop, executed by a whole 256-thread CTA: the stand-alone kernel below and the tail of
 // K1 (the last CTA of a crop to finish) both call it.  `sm` = C + Cse floats of shared memory.
 // `partial` is read with ld.global.cg: it may have been written by other CTAs of the same launch.
+// the two FC layers of the gate, from the channel means in shared memory (`mean`: C floats, `hid`: Cse floats of scratch).
+// The arithmetic and its order do not depend on NT or on who calls it (se_gate_kernel, the ticket tail of K1, the
+// per-CTA tail of K1 for blocks whose tile is the whole image), so every route gives the same bits.
+template <int NT>
+__device__ __forceinline__ void se_gate_fc(const float* mean, float* hid, const float* __restrict__ w1t, const float* __restrict__ b1,
+                                           const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ gate_n,
+                                           int C, int Cse, float* gate_sm = nullptr) {
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int j = warp; j < Cse; j += NT / 32) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(mean[c], w1t[(long long)j * C + c], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) hid[j] = swish_f(s + b1[j]);
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += NT) {
+        float s = b2[c];
+        for (int j = 0; j < Cse; ++j) s = fmaf(hid[j], w2[(long long)j * C + c], s);
+        const float g = sigmoid_f(s);
+        gate_n[c] = g;
+        if (gate_sm) gate_sm[c] = g;      // may alias `mean`: the means are dead after the barrier above
+    }
+}
+
 template <bool COHERENT, int NT = 256>
 __device__ __forceinline__ void se_gate_crop(const float* __restrict__ partial_n, int tiles, float inv_hw,
                                              const float* __restrict__ w1t, const float* __restrict__ b1,
@@ -520,20 +546,7 @@ __device__ __forceinline__ void se_gate_crop(const float* __restrict__ partial_n
         mean[c] = ((s0 + s1) + (s2 + s3)) * inv_hw;
     }
     __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int j = warp; j < Cse; j += NT / 32) {
-        float s = 0.f;
-        for (int c = lane; c < C; c += 32) s = fmaf(mean[c], w1t[(long long)j * C + c], s);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) hid[j] = swish_f(s + b1[j]);
-    }
-    __syncthreads();
-    for (int c = tid; c < C; c += NT) {
-        float s = b2[c];
-        for (int j = 0; j < Cse; ++j) s = fmaf(hid[j], w2[(long long)j * C + c], s);
-        gate_n[c] = sigmoid_f(s);
-    }
+    se_gate_fc<NT>(mean, hid, w1t, b1, w2, b2, gate_n, C, Cse);
 }
 
 template <int NT>

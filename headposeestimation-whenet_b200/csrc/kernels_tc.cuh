@@ -324,6 +324,7 @@ int launch_pw_tc(cudaStream_t stream, const T* A, const void* Wt16, const float*
     else if (!swish && gate && !resid) TC(false, true, false);
     else if (!swish && gate && resid) TC(false, true, true);
     else if (!swish && !gate && !resid) TC(false, false, false);
+    else if (!swish && !gate && resid) TC(false, false, true);
     else return 1;
 #undef TC
     return 0;
@@ -476,6 +477,15 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = s_tmem_base;
 
+    // GATE == 1: byte offset of the gate row (crop) of each of the 8 rows this thread rescales, fixed for the whole K loop
+    uint32_t g_row[8];
+    if (GATE == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = (tid >> 3) + 16 * i;
+            g_row[i] = r < rows_valid ? (uint32_t)(((m0 + r) / hw - crop0) * K) * 4u : 0u;
+        }
+    }
     for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % n_stages;
         const uint32_t a_st = smem0 + s * stage_bytes, w_st = a_st + A_STAGE_BYTES;
@@ -496,11 +506,8 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
                         const uint32_t a0 = a_st + (r0 >> 3) * 1024 + (r0 & 7) * 128 + ((c ^ (r0 & 7)) << 4);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const int r = r0 + 16 * i;
-                            if (r < rows_valid) {
-                                const int cr = (m0 + r) / hw - crop0;
-                                sts128_(a0 + i * 2048, scale8s<T>(lds128(a0 + i * 2048), sG + (uint32_t)(cr * K + (kc0 + c) * 8) * 4));
-                            }
+                            if (r0 + 16 * i < rows_valid)
+                                sts128_(a0 + i * 2048, scale8s<T>(lds128(a0 + i * 2048), sG + g_row[i] + (uint32_t)((kc0 + c) * 8) * 4));
                         }
                     }
                 } else {
@@ -608,7 +615,7 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
 
 template <typename T>
 int launch_pw_tc2(cudaStream_t stream, const T* A, const void* Wt16, const float* bias, const float* gate, const T* resid,
-                  T* out, long long M, int K, int N, int hw, bool swish, int stage_cap = 0, int smem_budget_kb = 54) {
+                  T* out, long long M, int K, int N, int hw, bool swish, int stage_cap = 0, int smem_budget_kb = 54, int min_ctas = 296) {
     if (sizeof(T) != 2) return 1;
     if ((K & 7) || (N & 7) || M > 0x7fffffffLL) return 1;
     const bool per_crop = gate && hw >= 784;                 // gate on W, tiles stay inside a crop
@@ -623,7 +630,7 @@ int launch_pw_tc2(cudaStream_t stream, const T* A, const void* Wt16, const float
             ++parts;
         }
     }
-    while (n_tile > 48 && m_tiles * ((N + n_tile - 1) / n_tile) < 296) {
+    while (n_tile > 48 && m_tiles * ((N + n_tile - 1) / n_tile) < min_ctas) {
         const int parts = (N + n_tile - 1) / n_tile + 1;
         const int nt = ((N + parts - 1) / parts + 15) & ~15;
         if (nt >= n_tile) break;
@@ -635,7 +642,8 @@ int launch_pw_tc2(cudaStream_t stream, const T* A, const void* Wt16, const float
     const uint32_t idesc = make_idesc(std::is_same<T, __nv_bfloat16>::value, umma_n);
     const int nkb = (K + BK - 1) / BK;
     const size_t stage_bytes = A_STAGE_BYTES + (size_t)umma_n * BK * 2;
-    const size_t gate_bytes = gate ? (size_t)(per_crop ? 1 : 4) * K * 4 : 0;
+    const int gate_crops = per_crop ? 1 : std::min(4, (BM - 1) / hw + 2);      // crops one 128-row tile can touch
+    const size_t gate_bytes = gate ? (size_t)gate_crops * K * 4 : 0;
     const size_t out_bytes = (size_t)BM * ((size_t)(n_tile >> 3) | 1) * 16;
     int n_stages = nkb < 4 ? nkb : 4;
     if (stage_cap > 0 && n_stages > stage_cap) n_stages = stage_cap;
@@ -646,17 +654,18 @@ int launch_pw_tc2(cudaStream_t stream, const T* A, const void* Wt16, const float
     size_t smem = n_stages * stage_bytes + gate_bytes;
     if (smem < out_bytes) smem = out_bytes;
     smem += 1024;
-    if (smem > 200 * 1024) return 1;
+    if (smem > 225 * 1024) return 1;
     dim3 grid((unsigned)((N + n_tile - 1) / n_tile), (unsigned)m_tiles);
     const T* W = reinterpret_cast<const T*>(Wt16);
 #define TC2(SW, GA, RE)                                                                                              \
     do {                                                                                                             \
         auto kfn = pw_tc2_kernel<T, SW, GA, RE>;                                                                     \
-        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1; \
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024) != cudaSuccess) return -1; \
         kfn<<<grid, 128, smem, stream>>>(A, W, bias, gate, resid, out, (int)M, K, N, hw, n_tile, umma_n, tmem_cols, n_stages, tpc, idesc); \
     } while (0)
     if (swish && !gate && !resid) TC2(true, 0, false);
     else if (!swish && !gate && !resid) TC2(false, 0, false);
+    else if (!swish && !gate && resid) TC2(false, 0, true);           // project conv whose input K1 has already gated
     else if (!swish && gate && !resid) { if (per_crop) TC2(false, 2, false); else TC2(false, 1, false); }
     else if (!swish && gate && resid) { if (per_crop) TC2(false, 2, true); else TC2(false, 1, true); }
     else return 1;

@@ -110,7 +110,7 @@ struct whenet_ctx {
     int use_tc = 0;         // tensor-core kernels for the 1x1 convs
     bool tc_used = false;   // a tcgen05 kernel ran since the last timeout-flag check
     int dw_variant = 1;     // 0 = one output per thread, 1 = register-blocked strips
-    int pw_stage_cap = 0, pw_smem_kb = 54;    // pw_tc2 ring: max stages (0 = up to 4) and per-CTA smem budget that trades depth for co-residency
+    int pw_stage_cap = 0, pw_smem_kb = 54, pw_min_ctas = 148;    // pw_tc2 ring: max stages (0 = up to 4) and per-CTA smem budget that trades depth for co-residency
     int pw_variant = 2;     // tensor-core 1x1 kernel: 1 = register-staged 2-stage ring, 2 = cp.async ring + in-smem SE gate
     int stem_variant = 1;   // 0 = 4 threads / pixel straight from global, 1 = smem-tiled, weights in the constant bank
     whenet::StemParams stem_params{};
@@ -153,6 +153,10 @@ struct whenet_ctx {
     int se_wide = 0;               // 1024-thread SE gate CTAs also for large batches
     int se_variant = 0;            // 1 = eight crops per CTA share one pass over the SE weights; measured SLOWER on B200
                                    // (0.71 vs 0.47 ms per 512 crops: 64 fat CTAs lose to 512 thin ones), kept as an option
+    int se_scale_out = 1;          // ... and gate their depthwise output in place, so the project conv runs without a gate pass
+    int k1_split_ctas = 120;       // small batches: split a crop's chunks over CTAs until the K1 grid has this many (measured: at 256
+                                   // crops per stream the late blocks run faster unsplit, with the SE tail, than split to 296)
+    int se_tail = 1;               // K1 CTAs that hold whole crops (blocks 7-16 at large batch) compute the SE gate themselves
     int se_fused = 0;              // K1's/K0's last CTA per crop computes the SE gate (no se_gate launch).  Measured on
                                    // B200 (round 1): the fence + ticket tail costs more (+0.7 ms / 512 crops) than the 15
                                    // small se_gate launches it saves (0.37 ms), so it is off by default.
@@ -303,7 +307,7 @@ int launch_pw(whenet_ctx* c, const char* name, const T* A, const float* W, const
     Scope sc(c, name, bytes, flops);
     if constexpr (sizeof(T) == 2) {
         if (c->use_tc && Wt16) {
-            int rc = c->pw_variant == 2 ? whenet::tc::launch_pw_tc2<T>(c->stream, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish, c->pw_stage_cap, c->pw_smem_kb)
+            int rc = c->pw_variant == 2 ? whenet::tc::launch_pw_tc2<T>(c->stream, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish, c->pw_stage_cap, c->pw_smem_kb, c->pw_min_ctas)
                                         : whenet::tc::launch_pw_tc<T>(c->stream, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish);
             if (rc == 0) { CK(cudaGetLastError()); c->tc_used = true; return 0; }
             if (rc < 0) return fail(WHENET_ECUDA, "tensor-core 1x1 launch failed for %s (rc=%d)", name, rc);
@@ -316,6 +320,7 @@ int launch_pw(whenet_ctx* c, const char* name, const T* A, const float* W, const
     else if (!swish && gate && !resid) PW(false, true, false);
     else if (!swish && gate && resid) PW(false, true, true);
     else if (!swish && !gate && !resid) PW(false, false, false);
+    else if (!swish && !gate && resid) PW(false, false, true);
     else return fail(WHENET_EINVAL, "unsupported 1x1 epilogue combination");
 #undef PW
     CK(cudaGetLastError());
@@ -396,7 +401,8 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
         const T* dw_in = cur;
         int tiles = 0;
         bool did_k1 = false;
-        bool se_in_k1 = false;      // the SE gate came out of the fused kernel's tail (option se_fused)
+        bool se_in_k1 = false;      // the SE gate came out of the fused kernel's tail (options se_fused / se_tail)
+        bool d_gated = false;       // ... and D already carries it
         if (i == 0 && did_k0) { did_k1 = true; se_in_k1 = c->se_fused != 0; tiles = 64; }      // K0 already produced D, the partials and the gate
         if constexpr (sizeof(T) == 2) {
             if (i == 0 && !did_k1 && c->use_fused && c->dw1_fused && c->dw1.valid) {
@@ -434,8 +440,17 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
                 {
                     const long long ctas = (long long)p.tiles_x * p.tiles_y * ((nb + p.NB - 1) / p.NB);
                     int split = 1;
-                    while (split < p.n_chunks && ctas * split < 296) ++split;
+                    while (split < p.n_chunks && ctas * split < c->k1_split_ctas) ++split;
                     p.chunks_per_cta = (p.n_chunks + split - 1) / split;
+                    // one tile per image and no chunk split: the CTA sees every pixel and channel of its crops and
+                    // computes their SE gate in its tail (same bits as se_gate_kernel, which is then not launched)
+                    if (c->se_tail && !se_in_k1 && p.tiles_x * p.tiles_y == 1 && split == 1) {
+                        p.se_tail = 1;
+                        p.inv_hw = 1.0f / (float)(b.hout * b.hout);
+                        se_in_k1 = true;
+                        // ... and applies it to its depthwise output (not under taps: the dw tap is the ungated tensor)
+                        if (c->se_scale_out && !taps) { p.scale_out = 1; d_gated = true; }
+                    }
                 }
                 snprintf(nm, sizeof nm, "b%02d.k1", b.idx);
                 Scope sc(c, nm, (double)nb * ((double)b.hin * b.hin * b.cin + (double)b.hout * b.hout * b.cexp) * sizeof(T),
@@ -478,7 +493,7 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
             CK(cudaGetLastError());
         }
         snprintf(nm, sizeof nm, "b%02d.project", b.idx);
-        rc = launch_pw<T>(c, nm, D, w.w_proj, w.wt_proj, w.b_proj, c->d_gate, b.skip ? cur : nullptr, oth,
+        rc = launch_pw<T>(c, nm, D, w.w_proj, w.wt_proj, w.b_proj, d_gated ? nullptr : c->d_gate, b.skip ? cur : nullptr, oth,
                           (long long)nb * b.hout * b.hout, b.cexp, b.cout, b.hout * b.hout, false);
         if (rc) return rc;
         if (taps) {
@@ -511,7 +526,7 @@ void drop_graphs(whenet_ctx* c) {
 }
 
 int options_signature(const whenet_ctx* c) {
-    return c->chunk * 1000003 + c->se_variant * 5 + c->dw1_fused * 3 + c->k1_variant * 16384 + c->k1t_max_block * 65536 + c->use_k0 * 8192 + c->se_fused * 4096 + c->use_tc * 64 + c->dw_variant * 32 + c->use_fused * 16 + c->stem_variant * 8 + c->pw_variant * 2 + c->fused_max_block * 128;
+    return c->chunk * 1000003 + c->se_tail * 1000 + c->se_scale_out * 2000 + c->k1_split_ctas * 13 + c->pw_min_ctas * 7 + c->pw_smem_kb * 11 + c->se_variant * 5 + c->dw1_fused * 3 + c->k1_variant * 16384 + c->k1t_max_block * 65536 + c->use_k0 * 8192 + c->se_fused * 4096 + c->use_tc * 64 + c->dw_variant * 32 + c->use_fused * 16 + c->stem_variant * 8 + c->pw_variant * 2 + c->fused_max_block * 128;
 }
 
 template <typename T, bool IN_U8>
@@ -1177,6 +1192,9 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!strcmp(key, "tensor_cores")) { c->use_tc = value && c->precision != WHENET_PRECISION_FP32; return 0; }
     if (!strcmp(key, "streams")) { c->n_streams = value < 1 ? 1 : (value > 4 ? 4 : value); return 0; }
     if (!strcmp(key, "se_fused")) { c->se_fused = value; return 0; }
+    if (!strcmp(key, "se_tail")) { c->se_tail = value; return 0; }
+    if (!strcmp(key, "se_scale_out")) { c->se_scale_out = value; return 0; }
+    if (!strcmp(key, "k1_split_ctas")) { c->k1_split_ctas = value; return 0; }
     if (!strcmp(key, "se_variant")) { c->se_variant = value; return 0; }
     if (!strcmp(key, "se_wide")) { c->se_wide = value; return 0; }
     if (!strcmp(key, "k0")) { c->use_k0 = value && c->precision != WHENET_PRECISION_FP32; return 0; }
@@ -1190,6 +1208,7 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!strcmp(key, "k1t_max_block")) { c->k1t_max_block = value; return 0; }
     if (!strcmp(key, "pw_stage_cap")) { c->pw_stage_cap = value; return 0; }
     if (!strcmp(key, "pw_smem_kb")) { c->pw_smem_kb = value; return 0; }
+    if (!strcmp(key, "pw_min_ctas")) { c->pw_min_ctas = value; return 0; }
     if (!strcmp(key, "fused")) { c->use_fused = value && c->precision != WHENET_PRECISION_FP32; return 0; }
     if (!strcmp(key, "fused_max_block")) { c->fused_max_block = value; return 0; }
     if (!strcmp(key, "chunk")) {

@@ -154,8 +154,9 @@ int64_t whenet_launch_count(whenet_ctx* ctx);
  *   "tensor_cores"   0: CUDA-core kernels for every 1x1 conv, 1: tcgen05 (default 1 for bf16/fp16, fp32 is always 0)
  *   "fused"          1: K1 (expand + depthwise fused, expanded tensor in shared memory) for blocks 2..fused_max_block
  *   "fused_max_block", "dw1_fused", "k1_variant" (2 = K1T, depthwise on the tensor core), "k1t_max_block",
- *   "k0" (stem + block-1 depthwise fused), "se_fused", "se_variant", "se_wide",
- *   "pw_variant" (1 register-staged ring, 2 cp.async ring), "pw_stage_cap", "pw_smem_kb",
+ *   "k0" (stem + block-1 depthwise fused), "se_fused", "se_tail" (K1 CTAs that hold whole crops compute the
+ *   SE gate themselves, default 1), "se_variant", "se_wide",
+ *   "pw_variant" (1 register-staged ring, 2 cp.async ring), "pw_stage_cap", "pw_smem_kb", "pw_min_ctas" (split N until the grid has this many CTAs),
  *   "dw_variant", "stem_variant", "host_chunk".
  * Unknown keys return WHENET_ENOTFOUND. */
 int whenet_set_option(whenet_ctx* ctx, const char* key, int value);

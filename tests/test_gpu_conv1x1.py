@@ -99,3 +99,18 @@ def test_conv1x1_tc_row_tails(net, M):
     for fam in (1, 2):
         a = net.debug_conv1x1(A, W, bias, use_tc=fam)
         assert np.abs(a - b).max() <= 2.0 ** -6 * max(1.0, np.abs(b).max())
+
+
+@pytest.mark.parametrize("use_tc", [0, 1, 2])
+@pytest.mark.parametrize("K,N", [(480, 80), (1152, 192)])
+def test_conv1x1_residual_without_gate(net, use_tc, K, N):
+    """Project conv of a block whose depthwise output was already gated by K1's tail: bias + residual, no gate."""
+    rng = np.random.default_rng(K + N)
+    M = 5 * 49 + 17
+    A = _bf16_round(rng.standard_normal((M, K)))
+    W = _bf16_round(rng.standard_normal((K, N)) / np.sqrt(K))
+    bias = rng.standard_normal(N).astype(np.float32)
+    resid = _bf16_round(rng.standard_normal((M, N)))
+    got = net.debug_conv1x1(A, W, bias, gate=None, resid=resid, hw=49, swish=False, use_tc=use_tc)
+    ref = A.astype(np.float64) @ W.astype(np.float64) + bias + resid
+    assert np.abs(got - ref).max() <= 2.5e-2 * max(1.0, np.abs(ref).max())

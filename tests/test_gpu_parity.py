@@ -223,6 +223,46 @@ def test_fused_k1_plan_variants(prec, plan_set, oracle32, sample_crops, jitter_c
     m.close()
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_se_tail_paths_bitwise(prec, oracle32, sample_crops, jitter_crops):
+    """Blocks whose K1 CTA holds whole crops compute the SE gate in the kernel tail and gate their depthwise output in
+    place.  Both steps must reproduce the stand-alone route (se_gate_kernel + gate pass inside the project conv) bit for
+    bit, because small batches (chunk split) still take that route; gates are also checked against the oracle."""
+    import whenet_b200
+    crops = np.concatenate([sample_crops, jitter_crops[:3]])          # 5 crops: the last two-crop CTA is half empty
+    m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=8)
+    m.set_option("se_tail", 0)
+    ref = np.stack(m.get_angle(crops), axis=1)
+    m.set_option("se_tail", 1)
+    m.set_option("k1_split_ctas", 0)           # no chunk split even at 5 crops -> the tail path runs
+    m.set_option("se_scale_out", 0)
+    launches0 = m.launch_count()
+    a = np.stack(m.get_angle(crops), axis=1)
+    n_tail = m.launch_count() - launches0
+    assert np.array_equal(a, ref)
+    m.set_option("se_scale_out", 1)
+    b = np.stack(m.get_angle(crops), axis=1)
+    assert np.array_equal(b, ref)
+    m.set_option("se_tail", 0)
+    launches0 = m.launch_count()
+    m.get_angle(crops)
+    assert m.launch_count() - launches0 == n_tail + 10      # blocks 7..16 lose their se_gate launch under se_tail
+    m.set_option("se_tail", 1)
+    taps = {}
+    oracle32.get_angle(crops, taps)
+    m.enable_taps(True)
+    m.get_angle(crops)
+    lim = 0.12 if prec == "bf16" else 0.02
+    for i in range(1, 17):
+        for kind in ("dw", "gate", "block"):
+            nm = "%s%d" % (kind, i)
+            r = taps[nm].astype(np.float64).reshape(-1)
+            g = m.tap(nm).astype(np.float64)
+            e = float(np.sqrt(((g - r) ** 2).mean()) / (np.sqrt((r ** 2).mean()) + 1e-30))
+            assert e < lim, (nm, e)
+    m.close()
+
+
 def test_fused_k1_batch_invariance(sample_crops, jitter_crops):
     import whenet_b200
     crops = np.concatenate([sample_crops, jitter_crops] * 3)[:19]
