@@ -183,9 +183,10 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(con
         // ---- E <- the input halo tile itself (Cin == Cexp == CC), zero outside the image (depthwise SAME padding)
         const T* in_n = in + (long long)n0 * p.Hin * p.Hin * p.Cin;
         const int cpp = CC >> 3;                                  // 16-byte chunks per pixel
+        const float inv_cpp = 1.0f / (float)cpp, inv_IW = 1.0f / (float)p.IW;
         for (int idx = tid; idx < npix * cpp; idx += NT) {
-            const int r = idx / cpp, c = idx - r * cpp;
-            const int ty = r / p.IW, tx = r - ty * p.IW;
+            const int r = div_small(idx, inv_cpp), c = idx - r * cpp;
+            const int ty = div_small(r, inv_IW), tx = r - ty * p.IW;
             const int iy = iy0 + ty, ix = ix0 + tx;
             const bool valid = iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Hin;
             cp_async16(sE + (uint32_t)r * pitchE + c * 16, valid ? in_n + ((long long)iy * p.Hin + ix) * p.Cin + c * 8 : in_n, valid);

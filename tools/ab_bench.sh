@@ -5,7 +5,7 @@ i=0
 for set in "$@"; do
   args=""
   for kv in $set; do args="$args --opt $kv"; done
-  python bench.py --no-cpu --steps 20 --warmup 5 $args > gpurun_out/ab_${tag}_$i.json 2> gpurun_out/ab_${tag}_$i.err
+  python bench.py --no-cpu --steps ${STEPS:-20} --warmup 5 --batch ${BATCH:-512} $args > gpurun_out/ab_${tag}_$i.json 2> gpurun_out/ab_${tag}_$i.err
   python - "$set" gpurun_out/ab_${tag}_$i.json <<'PY'
 import json, sys
 try:

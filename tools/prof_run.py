@@ -11,6 +11,10 @@ m.set_option("chunk", n)
 for k, v in (("tensor_cores", "TC"), ("dw_variant", "DWV"), ("fused", "FUSED"), ("streams", "STREAMS")):
     if v in os.environ:
         m.set_option(k, int(os.environ[v]))
+for kv in os.environ.get("OPTS", "").split(","):
+    if "=" in kv:
+        k, v = kv.split("=")
+        m.set_option(k, int(v))
 x = np.random.default_rng(0).integers(0, 256, (n, 224, 224, 3), dtype=np.uint8)
 for _ in range(reps):
     m.get_angle(x)
