@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(con
 
     const int n0 = blockIdx.y * p.NB, tile = blockIdx.x;
     const int nb_here = min(p.NB, p.N - n0);                                       // crops of this CTA
-    const int tyi = tile / p.tiles_x;
+    const int tyi = div_small(tile, 1.0f / (float)p.tiles_x);
     const int ty0 = tyi * p.TH, tx0 = (tile - tyi * p.tiles_x) * p.TW;             // output-tile origin
     const int iy0 = ty0 * S - p.pad, ix0 = tx0 * S - p.pad;                       // input-tile origin (may be < 0)
     const int npix = p.IH * p.IW;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(con
     // depthwise: thread = (4-channel vector cv, strip lane py); with NB crops per CTA the lanes split evenly between them
     const int CVc = CC >> 2;
     const int py = tid / CVc, cv = tid - py * CVc;
-    const int jc = py / p.PYc, pl = py - jc * p.PYc;               // crop of this lane, lane within the crop
+    const int jc = p.NB == 1 ? 0 : div_small(py, 1.0f / (float)p.PYc), pl = py - jc * p.PYc;   // crop of this lane, lane within the crop
     const bool dw_active = py < p.PY && jc < nb_here;
     const int nstrips = p.TH << p.spr_log2;
     const uint32_t e_rowstride = (uint32_t)p.IW * pitchE;
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(con
         }
         __syncthreads();
         if (ok && tid < p.NB * CC) {
-            const int jj = tid / CC, cc = tid - jj * CC;
+            const int jj = tid >= CC ? 1 : 0, cc = tid - jj * CC;          // NB <= 2
             if (jj < nb_here) {
                 // four independent chains (lane mod 4) keep this short: the two warps doing it are the ones every other warp
                 // waits for at the next barrier.  Fixed association order -> reproducible bits.

@@ -338,6 +338,9 @@ int launch_pw_tc(cudaStream_t stream, const T* A, const void* Wt16, const float*
 //       GATE == 1: on the A rows (tiles may span up to four crops; their gate rows sit in smem)
 //       GATE == 2: on the W rows (per-crop tiling: a tile never leaves its crop, used while H*W >= 784)
 //   * stage reuse is gated by the mbarrier of the previous block's tcgen05.commit.
+// exact floor(x / d) for small non-negative ints (x < 2^17, d < 2^8) with inv = 1.0f / d: (x + 0.5) / d is at least 0.5 / d
+// away from every integer, far more than the float rounding error - replaces the ~20-instruction integer division
+__device__ __forceinline__ int fdiv_small(int x, float inv) { return __float2int_rz(((float)x + 0.5f) * inv); }
 __device__ __forceinline__ void cp_async16_z(uint32_t dst, const void* src, bool valid) {
     const uint32_t sz = valid ? 16u : 0u;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
@@ -456,13 +459,13 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
             return;
         }
         for (int idx = tid; idx < BM * cbp; idx += 128) {
-            const int r = idx / cbp, c = idx - r * cbp;
+            const int r = fdiv_small(idx, 1.0f / (float)cbp), c = idx - r * cbp;
             const bool valid = r < rows_valid && c < cb;
             cp_async16_z(a_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4),
                          valid ? A + (long long)(m0 + r) * K + (kc0 + c) * 8 : A, valid);
         }
         for (int idx = tid; idx < umma_n * cbp; idx += 128) {
-            const int r = idx / cbp, c = idx - r * cbp;
+            const int r = fdiv_small(idx, 1.0f / (float)cbp), c = idx - r * cbp;
             const bool valid = r < n_valid && c < cb;
             cp_async16_z(w_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4),
                          valid ? Wt + (long long)(n0 + r) * K + (kc0 + c) * 8 : Wt, valid);
@@ -512,7 +515,7 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
                     }
                 } else {
                     for (int idx = tid; idx < BM * cbp; idx += 128) {
-                        const int r = idx / cbp, c = idx - r * cbp;
+                        const int r = fdiv_small(idx, 1.0f / (float)cbp), c = idx - r * cbp;
                         if (r < rows_valid && c < cb) {
                             const uint32_t addr = a_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
                             const int cr = (m0 + r) / hw - crop0;
@@ -530,7 +533,7 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
                         }
                 } else {
                     for (int idx = tid; idx < umma_n * cbp; idx += 128) {
-                        const int r = idx / cbp, c = idx - r * cbp;
+                        const int r = fdiv_small(idx, 1.0f / (float)cbp), c = idx - r * cbp;
                         if (r < n_valid && c < cb) {
                             const uint32_t addr = w_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
                             sts128_(addr, scale8s<T>(lds128(addr), sG + (uint32_t)((kc0 + c) * 8) * 4));
@@ -569,6 +572,7 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
 
     // ---- epilogue (as in pw_tc_kernel): TMEM -> +shift, swish, +residual -> 16-bit -> stage -> coalesced stores
     const int nch = n_valid >> 3;
+    const float inv_nch = 1.0f / (float)(nch > 0 ? nch : 1);
     const int pitch16 = nch | 1;
     uint4* stage = reinterpret_cast<uint4*>(smem_raw + (smem0 - smem_u32(smem_raw)));
     const bool row_ok = tid < rows_valid;
@@ -603,7 +607,7 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
     __syncthreads();
     if (!s_abort) {
         for (int idx = tid; idx < rows_valid * nch; idx += 128) {
-            const int r = idx / nch, j = idx - r * nch;
+            const int r = fdiv_small(idx, inv_nch), j = idx - r * nch;
             *reinterpret_cast<uint4*>(out + ((long long)m0 + r) * N + n0 + j * 8) = stage[r * pitch16 + j];
         }
     }
