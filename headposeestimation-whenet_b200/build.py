@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwhenet_b200.so")
 SOURCES = ["whenet_api.cu"]
-HEADERS = ["kernels_simt.cuh", "kernels_tc.cuh", "kernels_fused.cuh", "kernels_fused_tc.cuh", "kernels_crop.cuh", "kernels_k0.cuh", os.path.join("..", "..", "include", "whenet_b200.h")]
+HEADERS = ["kernels_simt.cuh", "kernels_tc.cuh", "kernels_fused.cuh", "kernels_fused_tc.cuh", "kernels_crop.cuh", "kernels_k0.cuh", "kernels_k1p.cuh", os.path.join("..", "..", "include", "whenet_b200.h")]
 
 # no --use_fast_math: precise expf / division are required by the fp32 parity mode
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -22,6 +22,7 @@
 #include "kernels_fused_tc.cuh"
 #include "kernels_crop.cuh"
 #include "kernels_k0.cuh"
+#include "kernels_k1p.cuh"
 
 namespace {
 
@@ -91,6 +92,7 @@ struct BlockW {   // device pointers into the fp32 arena
 };
 
 struct K1Plan { bool valid = false; whenet::fused::K1Params p{}; int R = 0; int NT = 256; size_t smem = 0; };
+struct K1PPlan { bool valid = false; whenet::fused::K1PParams p{}; int R = 0; size_t smem = 0; };
 struct K1TPlan { bool valid = false; whenet::fused::K1TParams p{}; size_t smem = 0; };
 struct GraphKey {
     int n, in_u8, sig;
@@ -128,6 +130,10 @@ struct whenet_ctx {
     int fused_max_block = 16;  // blocks 2..fused_max_block use K1
     std::vector<K1Plan> k1;
     std::vector<K1TPlan> k1t;
+    std::vector<K1PPlan> k1p;  // k1_variant 3: persistent warp-specialised K1 for the blocks with several tiles per crop
+    int sm_count = 148;
+    int k1p_epi_warps = 8;     // epilogue group of K1P: 4 or 8 warps (the depthwise group gets the other 10 or 6)
+    int k1p_min_crops = 8;     // below this a persistent grid cannot fill the SMs: K1 with its chunk split is used instead
     K1Plan dw1;                // block 1 (no expand): depthwise-only instance of K1
     int dw1_fused = 1;
     int k1_variant = 1;        // 1 = K1 (depthwise on CUDA cores), 2 = K1T (depthwise on the tensor core via diagonal weights)
@@ -429,6 +435,19 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
                 CK(cudaGetLastError());
                 c->tc_used = true;
                 tiles = p.tiles_x * p.tiles_y;
+                did_k1 = true;
+            } else if (c->use_fused && c->k1_variant == 3 && c->k1p[i].valid && nb >= c->k1p_min_crops && b.idx <= c->fused_max_block) {
+                whenet::fused::K1PParams pp = c->k1p[i].p;
+                whenet::fused::K1Params& p = pp.k;
+                p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial;
+                snprintf(nm, sizeof nm, "b%02d.k1", b.idx);
+                Scope sc(c, nm, (double)nb * ((double)b.hin * b.hin * b.cin + (double)b.hout * b.hout * b.cexp) * sizeof(T),
+                         2.0 * nb * ((double)b.hin * b.hin * b.cin * b.cexp + (double)b.hout * b.hout * b.k * b.k * b.cexp));
+                int rc = whenet::fused::launch_k1p<T>(c->stream, pp, b.k, b.s, c->k1p[i].R, c->k1p[i].smem, nb, c->sm_count);
+                if (rc != 0) return fail(WHENET_ECUDA, "K1P launch failed for block %d (rc=%d)", b.idx, rc);
+                CK(cudaGetLastError());
+                c->tc_used = true;
+                tiles = pp.tiles;
                 did_k1 = true;
             } else if (c->use_fused && c->k1[i].valid && b.idx <= c->fused_max_block) {
                 whenet::fused::K1Params p = c->k1[i].p;
@@ -735,6 +754,7 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
     c->device = device;
     c->max_batch = max_batch;
     c->precision = precision;
+    c->sm_count = prop.multiProcessorCount;
     const char* ev = getenv("WHENET_CHUNK");
     int chunk = ev ? atoi(ev) : max_batch;   // one pass over the whole batch is fastest (8.2 ms vs 13 ms per 512 crops at chunk 128)
     if (chunk < 1) chunk = max_batch;
@@ -745,6 +765,7 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
     c->bw.resize(c->blocks.size());
     c->k1.resize(c->blocks.size());
     c->k1t.resize(c->blocks.size());
+    c->k1p.resize(c->blocks.size());
     if (precision != WHENET_PRECISION_FP32) {
         const BlockCfg& b1 = c->blocks[0];
         c->dw1.valid = !b1.has_expand && whenet::fused::plan_dw_only(b1.hin, b1.cexp, b1.k, b1.s, b1.pad, &c->dw1.p, &c->dw1.smem);
@@ -760,6 +781,12 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
                                               &pl.p, &ch, &pl.smem);
             pl.R = ch.r;
             pl.NT = ch.nt;
+            if (pl.valid && pl.p.tiles_x * pl.p.tiles_y > 1) {       // K1P: same tile, strip and chunk shape as the K1 plan
+                K1PPlan& pq = c->k1p[i];
+                pq.valid = whenet::fused::plan_k1p(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, precision == WHENET_PRECISION_BF16,
+                                                   pl.p.TH, pl.p.TW, pl.R, pl.p.CC, c->k1p_epi_warps, &pq.p, &pq.smem);
+                pq.R = pl.R;
+            }
             K1TPlan& pt = c->k1t[i];
             pt.valid = whenet::fused::plan_k1t(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, precision == WHENET_PRECISION_BF16,
                                                &pt.p, &pt.smem);
@@ -1195,6 +1222,23 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!strcmp(key, "se_tail")) { c->se_tail = value; return 0; }
     if (!strcmp(key, "se_scale_out")) { c->se_scale_out = value; return 0; }
     if (!strcmp(key, "k1_split_ctas")) { c->k1_split_ctas = value; return 0; }
+    if (!strcmp(key, "k1p_min_crops")) { c->k1p_min_crops = value; return 0; }
+    if (!strcmp(key, "k1p_epi_warps")) {
+        if (value != 4 && value != 8) return fail(WHENET_EINVAL, "k1p_epi_warps is 4 or 8");
+        c->k1p_epi_warps = value;
+        for (size_t i = 0; i < c->blocks.size(); ++i) {       // re-plan: the strip-lane count depends on the group sizes
+            const BlockCfg& b = c->blocks[i];
+            const K1Plan& pl = c->k1[i];
+            K1PPlan& pq = c->k1p[i];
+            pq.valid = false;
+            if (pl.valid && pl.p.tiles_x * pl.p.tiles_y > 1) {
+                pq.valid = whenet::fused::plan_k1p(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, c->precision == WHENET_PRECISION_BF16,
+                                                   pl.p.TH, pl.p.TW, pl.R, pl.p.CC, value, &pq.p, &pq.smem);
+                pq.R = pl.R;
+            }
+        }
+        return 0;
+    }
     if (!strcmp(key, "se_variant")) { c->se_variant = value; return 0; }
     if (!strcmp(key, "se_wide")) { c->se_wide = value; return 0; }
     if (!strcmp(key, "k0")) { c->use_k0 = value && c->precision != WHENET_PRECISION_FP32; return 0; }

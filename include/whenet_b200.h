@@ -153,7 +153,8 @@ int64_t whenet_launch_count(whenet_ctx* ctx);
  *   "graph"          1: replay device-resident forwards from a captured CUDA graph (default 0)
  *   "tensor_cores"   0: CUDA-core kernels for every 1x1 conv, 1: tcgen05 (default 1 for bf16/fp16, fp32 is always 0)
  *   "fused"          1: K1 (expand + depthwise fused, expanded tensor in shared memory) for blocks 2..fused_max_block
- *   "fused_max_block", "dw1_fused", "k1_variant" (2 = K1T, depthwise on the tensor core), "k1t_max_block",
+ *   "fused_max_block", "dw1_fused", "k1_variant" (2 = K1T, depthwise on the tensor core; 3 = K1P, persistent
+ *   warp-specialised K1 for blocks 2-6), "k1p_epi_warps" (4 or 8), "k1p_min_crops", "k1_split_ctas", "k1t_max_block",
  *   "k0" (stem + block-1 depthwise fused), "se_fused", "se_tail" (K1 CTAs that hold whole crops compute the
  *   SE gate themselves, default 1), "se_variant", "se_wide",
  *   "pw_variant" (1 register-staged ring, 2 cp.async ring), "pw_stage_cap", "pw_smem_kb", "pw_min_ctas" (split N until the grid has this many CTAs),
