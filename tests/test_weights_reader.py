@@ -91,3 +91,27 @@ def test_h5_reader_rejects_garbage(tmp_path):
     p.write_bytes(b"not an hdf5 file at all")
     with pytest.raises(h5lite.H5FormatError):
         h5lite.H5File(str(p))
+
+
+def test_safetensors_artefact_round_trip(tmp_path):
+    """The persisted artefact: same tensors bit for bit, layer order kept, loadable as a snapshot."""
+    from whenet_b200 import stlite, weights
+    names, w = weights.load_snapshot(SNAP)
+    path = os.path.join(tmp_path, "whenet.safetensors")
+    weights.save_safetensors(path, names, w)
+    names2, w2 = weights.load_snapshot(path)
+    assert names2 == names and sorted(w2) == sorted(w)
+    for k in w:
+        assert w2[k].dtype == np.float32 and w2[k].shape == w[k].shape and np.array_equal(w2[k].view(np.uint32), w[k].view(np.uint32)), k
+    raw, meta = stlite.load(path)
+    assert meta["format"] == "whenet-keras-raw-f32" and len(raw) == 315
+    # container checks: truncated data, bad header length, non-JSON header
+    blob = open(path, "rb").read()
+    bad = os.path.join(tmp_path, "bad.safetensors")
+    for mutated in (blob[:len(blob) - 4096], b"\xff" * 8 + blob[8:], blob[:8] + b"{" * 64 + blob[72:]):
+        with open(bad, "wb") as f:
+            f.write(mutated)
+        with pytest.raises(ValueError):
+            stlite.load(bad)
+    with pytest.raises(ValueError):
+        stlite.save(bad, {"x": np.zeros(3, dtype=np.complex64)})

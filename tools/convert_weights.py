@@ -1,4 +1,4 @@
-"""Convert the reference's Keras ``WHENet.h5`` into a plain ``.npz``.
+"""Convert the reference's Keras ``WHENet.h5`` into a plain ``.npz`` (or, by extension, ``.safetensors``).
 
 ``/root/reference`` does not exist on the GPU box, so the weights the parity
 tests need must travel inside the repo.  The ``.npz`` holds the 315 float32
@@ -19,6 +19,13 @@ import h5lite  # noqa: E402
 
 
 def main(src, dst):
+    if dst.endswith(".safetensors"):
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+        from whenet_b200 import weights as wmod
+        names, w = wmod.load_snapshot(src)                 # .h5, .npz or .safetensors in
+        wmod.save_safetensors(dst, names, w)
+        print("wrote %s: %d tensors" % (dst, len(w)))
+        return
     layer_names, weights, meta = h5lite.read_keras_weights(src)
     out = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in weights.items()}
     out["__layer_names__"] = np.array(layer_names)
