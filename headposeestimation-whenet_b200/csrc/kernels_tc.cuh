@@ -31,7 +31,9 @@
 namespace whenet {
 namespace tc {
 
-__device__ int g_tc_timeout_flag = 0;
+// one copy per translation unit (the library is built from several, see build.py): kernels raise the flag of their own
+// unit and every unit exports a reader (whenet::tu_timeout_*), which the API unit polls after a forward
+static __device__ int g_tc_timeout_flag = 0;
 
 constexpr int BM = 128;          // pixels per CTA == TMEM lanes == UMMA M
 constexpr int BK = 64;           // channels per stage (one 128-byte swizzle row of 16-bit elements)
@@ -677,7 +679,7 @@ int launch_pw_tc2(cudaStream_t stream, const T* A, const void* Wt16, const float
     return 0;
 }
 
-inline int read_and_clear_timeout_flag() {
+static inline int read_and_clear_timeout_flag() {     // internal linkage on purpose: it reads THIS unit's flag
     int v = 0, z = 0;
     if (cudaMemcpyFromSymbol(&v, g_tc_timeout_flag, sizeof(int)) != cudaSuccess) return -1;
     if (v) cudaMemcpyToSymbol(g_tc_timeout_flag, &z, sizeof(int));

@@ -24,6 +24,30 @@
 #include "kernels_k0.cuh"
 #include "kernels_k1p.cuh"
 
+// The fused-kernel launchers are instantiated in their own translation units (inst_k1_bf16.cu, inst_k1_f16.cu, inst_k1x.cu)
+namespace whenet {
+namespace fused {
+#define WHENET_EXTERN_FUSED(T)                                                                            \
+    extern template int launch_k1<T>(cudaStream_t, K1Params, int, int, int, int, size_t, int);            \
+    extern template int launch_dw_only<T>(cudaStream_t, K1Params, size_t, int);                           \
+    extern template int launch_k1p<T>(cudaStream_t, K1PParams, int, int, int, size_t, int, int);          \
+    extern template int launch_k1t<T>(cudaStream_t, const K1TParams&, int, int, size_t, int);
+WHENET_EXTERN_FUSED(__nv_bfloat16)
+WHENET_EXTERN_FUSED(__half)
+#undef WHENET_EXTERN_FUSED
+}  // namespace fused
+int tu_timeout_k1_bf16();
+int tu_timeout_k1_f16();
+int tu_timeout_k1x();
+// any tcgen05 kernel of any unit timed out on an mbarrier since the last call (-1: the flag could not be read)
+static int any_tc_timeout() {
+    const int v[4] = {tc::read_and_clear_timeout_flag(), tu_timeout_k1_bf16(), tu_timeout_k1_f16(), tu_timeout_k1x()};
+    int r = 0;
+    for (int x : v) r = x < 0 ? (r ? r : -1) : (x ? 1 : r);
+    return r;
+}
+}  // namespace whenet
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -664,7 +688,7 @@ int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* a
         CK(cudaStreamSynchronize(c->stream));
         if (c->tc_used) {
             c->tc_used = false;
-            if (whenet::tc::read_and_clear_timeout_flag() != 0)
+            if (whenet::any_tc_timeout() != 0)
                 return fail(WHENET_ECUDA, "a tcgen05 kernel timed out waiting on an mbarrier (results invalid)");
         }
     }
@@ -1059,7 +1083,7 @@ int whenet_synchronize(whenet_ctx* c) {
     CK(cudaStreamSynchronize(c->stream));
     if (c->tc_used) {
         c->tc_used = false;
-        if (whenet::tc::read_and_clear_timeout_flag() != 0)
+        if (whenet::any_tc_timeout() != 0)
             return fail(WHENET_ECUDA, "a tcgen05 kernel timed out waiting on an mbarrier (results invalid)");
     }
     return 0;
@@ -1138,7 +1162,7 @@ int debug_conv_impl(whenet_ctx* c, int use_tc, const float* A, const float* W, c
     c->use_tc = saved;
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (rc == 0 && e != cudaSuccess) rc = fail(WHENET_ECUDA, "debug conv failed: %s", cudaGetErrorString(e));
-    if (rc == 0 && use_tc && whenet::tc::read_and_clear_timeout_flag() != 0) rc = fail(WHENET_ECUDA, "tcgen05 kernel timed out on an mbarrier");
+    if (rc == 0 && use_tc && whenet::any_tc_timeout() != 0) rc = fail(WHENET_ECUDA, "tcgen05 kernel timed out on an mbarrier");
     if (rc == 0) {
         e = cudaMemcpy(hO.data(), dO, hO.size() * sizeof(T), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = fail(WHENET_ECUDA, "copy back failed: %s", cudaGetErrorString(e));
