@@ -39,10 +39,12 @@ def _unit_stale(src: str) -> bool:
 
 
 def _stale() -> bool:
+    """The library is older than one of its sources (objects are a build cache: their absence alone triggers nothing)."""
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(_unit_stale(s) or os.path.getmtime(_obj(s)) > t for s in SOURCES)
+    deps = [os.path.join(CSRC, d) for d in SOURCES + HEADERS]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
