@@ -1206,6 +1206,22 @@ int whenet_debug_set_k1_plan(whenet_ctx* c, int block, int th, int tw, int r, in
     return 0;
 }
 
+int whenet_debug_set_k1p_plan(whenet_ctx* c, int block, int th, int tw, int r, int cc, int epi_warps) {
+    if (!c || block < 2 || block > (int)c->blocks.size()) return fail(WHENET_EINVAL, "bad block index");
+    if (c->precision == WHENET_PRECISION_FP32) return fail(WHENET_EINVAL, "K1P needs a 16-bit storage mode");
+    const BlockCfg& b = c->blocks[block - 1];
+    if (cc < 16 || cc > 128 || (cc & 15) || r < 1 || th < 1 || tw < 1) return fail(WHENET_EINVAL, "bad plan parameters");
+    if (!whenet::fused::k1_has_instance(b.k, b.s, r)) return fail(WHENET_EINVAL, "no K1P instantiation for k=%d s=%d r=%d", b.k, b.s, r);
+    K1PPlan pq;
+    pq.valid = whenet::fused::plan_k1p(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, c->precision == WHENET_PRECISION_BF16,
+                                       th, tw, r, cc, epi_warps, &pq.p, &pq.smem);
+    if (!pq.valid) return fail(WHENET_EINVAL, "K1P plan %dx%d r%d cc%d epi%d does not fit block %d", th, tw, r, cc, epi_warps, block);
+    pq.R = r;
+    c->k1p[block - 1] = pq;
+    free_ws(c);      // the squeeze-partials buffer depends on the tile count
+    return 0;
+}
+
 int whenet_profile_enable(whenet_ctx* c, int enable) {
     if (!c) return fail(WHENET_EINVAL, "null context");
     c->prof_on = enable != 0;

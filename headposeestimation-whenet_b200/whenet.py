@@ -249,6 +249,10 @@ class WHENet:
         """Tuning hook (see whenet_debug_set_k1_plan); returns False when the plan cannot run."""
         return self._L.whenet_debug_set_k1_plan(self._h, block, th, tw, r, cc, nt, nb) == 0
 
+    def set_k1p_plan(self, block: int, th: int, tw: int, r: int, cc: int, epi_warps: int = 8) -> bool:
+        """Tuning hook for the persistent variant (see whenet_debug_set_k1p_plan); False when the plan cannot run."""
+        return self._L.whenet_debug_set_k1p_plan(self._h, block, th, tw, r, cc, epi_warps) == 0
+
     def enable_profile(self, on: bool = True):
         check(self._L.whenet_profile_enable(self._h, int(on)))
 

@@ -139,6 +139,10 @@ int whenet_debug_conv1x1(whenet_ctx* ctx, int use_tc, const float* A, const floa
  * per CTA (2 only where one tile is the whole image).  WHENET_EINVAL if the plan cannot run. */
 int whenet_debug_set_k1_plan(whenet_ctx* ctx, int block, int th, int tw, int r, int cc, int nt, int nb);
 
+/* Same for K1P (option "k1_variant" = 3; blocks with several tiles per crop): tile, strip and chunk shape plus the
+ * size of the TMEM-epilogue warp group (4 or 8; the depthwise group gets the remaining warps of the 512-thread CTA). */
+int whenet_debug_set_k1p_plan(whenet_ctx* ctx, int block, int th, int tw, int r, int cc, int epi_warps);
+
 /* Time every kernel of the NEXT forwards with CUDA events. */
 int whenet_profile_enable(whenet_ctx* ctx, int enable);
 /* Read (and reset) the accumulated per-kernel statistics; returns the count written. */
