@@ -3,8 +3,8 @@
 usage: python tools/ncu_source.py report.ncu-rep out.txt [top_n]
 
 For every kernel in the report: warp instructions executed and warp-stall samples summed over the SASS of each source
-line, as a share of the kernel, top lines first; then the same grouped by a coarse phase label (looked up from
-PHASES, line ranges of kernels_fused.cuh / kernels_tc.cuh) when the file matches.  Small enough to commit under profiles/.
+line, as a share of the kernel, with the two dominant stall reasons of the line, top lines first.  Small enough to
+commit under profiles/.
 """
 import csv, io, subprocess, sys
 from collections import defaultdict
