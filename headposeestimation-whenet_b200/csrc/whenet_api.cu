@@ -39,11 +39,15 @@ WHENET_EXTERN_FUSED(__half)
 int tu_timeout_k1_bf16();
 int tu_timeout_k1_f16();
 int tu_timeout_k1x();
-// any tcgen05 kernel of any unit timed out on an mbarrier since the last call (-1: the flag could not be read)
+// any tcgen05 kernel of any unit timed out on an mbarrier since the last call (-1: this unit's flag could not be read).
+// A unit whose flag cannot be read is skipped (and the sticky CUDA error cleared) rather than failing every forward.
 static int any_tc_timeout() {
-    const int v[4] = {tc::read_and_clear_timeout_flag(), tu_timeout_k1_bf16(), tu_timeout_k1_f16(), tu_timeout_k1x()};
-    int r = 0;
-    for (int x : v) r = x < 0 ? (r ? r : -1) : (x ? 1 : r);
+    int r = tc::read_and_clear_timeout_flag();
+    const int others[3] = {tu_timeout_k1_bf16(), tu_timeout_k1_f16(), tu_timeout_k1x()};
+    for (int x : others) {
+        if (x < 0) cudaGetLastError();
+        else if (x > 0 && r == 0) r = 1;
+    }
     return r;
 }
 }  // namespace whenet
