@@ -12,7 +12,7 @@ PRECISIONS = {"fp32": 0, "bf16": 1, "fp16": 2}
 EXPORTS = [
     "whenet_create", "whenet_load_weights", "whenet_set_stream", "whenet_forward_u8", "whenet_forward_u8_async", "whenet_forward_f32",
     "whenet_crop_resize_u8", "whenet_synchronize", "whenet_host_alloc", "whenet_host_free", "whenet_debug_enable_taps", "whenet_debug_tap",
-    "whenet_debug_conv1x1", "whenet_debug_set_k1_plan", "whenet_debug_set_k1p_plan", "whenet_profile_enable", "whenet_profile_read", "whenet_launch_count", "whenet_set_option",
+    "whenet_debug_conv1x1", "whenet_debug_decode", "whenet_debug_raise_timeout", "whenet_debug_set_k1_plan", "whenet_debug_set_k1p_plan", "whenet_profile_enable", "whenet_profile_read", "whenet_launch_count", "whenet_set_option",
     "whenet_last_error", "whenet_version", "whenet_destroy",
 ]
 
@@ -49,7 +49,9 @@ def load():
         from . import build
         try:
             build.build_lib()
-        except Exception:
+        except FileNotFoundError:
+            # no nvcc on this machine: a prebuilt library is acceptable.  A COMPILE or LINK failure is not - loading the
+            # stale binary next to edited sources would run old kernels against new host code.
             if not os.path.exists(path):
                 raise
     if not os.path.exists(path):
@@ -71,6 +73,8 @@ def load():
     L.whenet_debug_enable_taps.argtypes = [P, C.c_int]
     L.whenet_debug_tap.argtypes = [P, C.c_char_p, P, C.c_size_t, C.POINTER(C.c_size_t)]
     L.whenet_debug_conv1x1.argtypes = [P, C.c_int, P, P, P, P, P, P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.whenet_debug_decode.argtypes = [P, P, C.c_int, P]
+    L.whenet_debug_raise_timeout.argtypes = [P]
     L.whenet_debug_set_k1_plan.argtypes = [P] + [C.c_int] * 7
     L.whenet_debug_set_k1p_plan.argtypes = [P] + [C.c_int] * 6
     L.whenet_profile_enable.argtypes = [P, C.c_int]

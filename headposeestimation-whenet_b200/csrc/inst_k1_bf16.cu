@@ -8,5 +8,4 @@ namespace fused {
 template int launch_k1<__nv_bfloat16>(cudaStream_t, K1Params, int, int, int, int, size_t, int);
 template int launch_dw_only<__nv_bfloat16>(cudaStream_t, K1Params, size_t, int);
 }  // namespace fused
-int tu_timeout_k1_bf16() { return tc::read_and_clear_timeout_flag(); }
 }  // namespace whenet

@@ -6,5 +6,4 @@ namespace fused {
 template int launch_k1<__half>(cudaStream_t, K1Params, int, int, int, int, size_t, int);
 template int launch_dw_only<__half>(cudaStream_t, K1Params, size_t, int);
 }  // namespace fused
-int tu_timeout_k1_f16() { return tc::read_and_clear_timeout_flag(); }
 }  // namespace whenet

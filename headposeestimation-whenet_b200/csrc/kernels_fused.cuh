@@ -72,6 +72,7 @@ struct K1Params {
     int spr_log2;          // log2(strips per output row)
     uint32_t idesc;
     int smem_A, smem_W, smem_C, smem_E;   // region sizes in bytes (W and C are per buffer; both double-buffered)
+    int* tflag;            // the context's mbarrier-timeout flag (mapped pinned host memory)
     int chunks_per_cta;    // grid.z CTAs share one tile, each takes this many consecutive chunks (small batches: more CTAs per crop)
 };
 
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(con
         const int buf = ch & 1;
         const int cbase = ch * CC;
         if (!NOEXP) {
-            if (!tc::mbar_wait(&mbar, (ch - ch_begin) & 1)) s_abort = 1;      // MMA(ch): issued one phase ago, normally long done
+            if (!tc::mbar_wait(&mbar, (ch - ch_begin) & 1, p.tflag)) s_abort = 1;      // MMA(ch): issued one phase ago, normally long done
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         // constants of chunk ch+1 (group 1), then W of chunk ch+2 into the buffer MMA(ch) has just released (group 2)

@@ -44,7 +44,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // bounded wait that degrades to a no-op once any thread of the CTA has timed out: the roles keep their control flow
 // (named barriers stay matched), the kernel finishes quickly with garbage, and the host sees the timeout flag
-__device__ __forceinline__ void k1p_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
+__device__ __forceinline__ void k1p_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int* tflag) {
     if (*abort_flag) return;
     const uint32_t addr = tc::smem_u32(bar);
     for (uint32_t it = 0; it < (1u << 20); ++it) {
@@ -58,7 +58,7 @@ __device__ __forceinline__ void k1p_wait(uint64_t* bar, uint32_t parity, volatil
         if ((it & 1023u) == 1023u && *abort_flag) return;
     }
     *abort_flag = 1;
-    atomicExch(&tc::g_tc_timeout_flag, 1);
+    *reinterpret_cast<volatile int*>(tflag) = 1;
 }
 
 // tcgen05.ld without the wait, and a wait that carries the destination registers as in/out operands so that no consumer
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(K1P_THREADS, 1) k1p_kernel(const K1PParams pp)
             const Geo g = geom(item);
             const int abuf = k & 1;
             const uint32_t a0 = sA + abuf * pp.smem_A1;
-            k1p_wait(&bar_a_empty[abuf], ((k >> 1) & 1) ^ 1, s_abort);      // the MMAs of item k-2 have finished reading this buffer
+            k1p_wait(&bar_a_empty[abuf], ((k >> 1) & 1) ^ 1, s_abort, p.tflag);      // the MMAs of item k-2 have finished reading this buffer
             const float inv_IWin = 1.0f / (float)g.IWin;
             const T* in_t = in + ((long long)g.n * p.Hin * p.Hin + (long long)(g.iy0 + g.ty_lo) * p.Hin + (g.ix0 + g.tx_lo)) * p.Cin;
             // one GEMM row (= one inside pixel, Cin contiguous values in global memory) per lane and step
@@ -199,17 +199,17 @@ __global__ void __launch_bounds__(K1P_THREADS, 1) k1p_kernel(const K1PParams pp)
         }
     } else if (warp == 1) {
         // =========================================================================== MMA issue
-        k1p_wait(&bar_const, 0, s_abort);
+        k1p_wait(&bar_const, 0, s_abort, p.tflag);
         const int ksteps_total = p.cpr >> 1;
         int k = 0, gi = 0;
         for (int item = blockIdx.x; item < pp.items; item += gridDim.x, ++k) {
             const Geo g = geom(item);
             const int abuf = k & 1;
-            k1p_wait(&bar_a_full[abuf], (k >> 1) & 1, s_abort);
+            k1p_wait(&bar_a_full[abuf], (k >> 1) & 1, s_abort, p.tflag);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int ch = 0; ch < n_chunks; ++ch, ++gi) {
                 const int tbuf = gi & 1;
-                k1p_wait(&bar_t_empty[tbuf], ((gi >> 1) & 1) ^ 1, s_abort);   // the epilogue has drained this accumulator
+                k1p_wait(&bar_t_empty[tbuf], ((gi >> 1) & 1) ^ 1, s_abort, p.tflag);   // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0 && !*s_abort) {
                     for (int mt = 0; mt < g.mtc; ++mt)
@@ -257,8 +257,8 @@ __global__ void __launch_bounds__(K1P_THREADS, 1) k1p_kernel(const K1PParams pp)
             const bool border = g.npix_in != npix;
             for (int ch = 0; ch < n_chunks; ++ch, ++gi) {
                 const int buf = gi & 1;
-                k1p_wait(&bar_t_full[buf], (gi >> 1) & 1, s_abort);
-                k1p_wait(&bar_e_empty[buf], ((gi >> 1) & 1) ^ 1, s_abort);     // the depthwise of chunk gi-2 has finished with this E
+                k1p_wait(&bar_t_full[buf], (gi >> 1) & 1, s_abort, p.tflag);
+                k1p_wait(&bar_e_empty[buf], ((gi >> 1) & 1) ^ 1, s_abort, p.tflag);     // the depthwise of chunk gi-2 has finished with this E
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t e0 = sE + buf * pp.smem_E1;
                 if (border && ch < 2) {
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(K1P_THREADS, 1) k1p_kernel(const K1PParams pp)
         const int nstrips = p.TH << p.spr_log2;
         const uint32_t e_rowstride = (uint32_t)p.IW * pitchE;
         constexpr int NCOL = (R - 1) * S + KS;
-        k1p_wait(&bar_const, 0, s_abort);
+        k1p_wait(&bar_const, 0, s_abort, p.tflag);
         int gi = 0;
         for (int item = blockIdx.x; item < pp.items; item += gridDim.x) {
             const Geo g = geom(item);
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(K1P_THREADS, 1) k1p_kernel(const K1PParams pp)
             for (int ch = 0; ch < n_chunks; ++ch, ++gi) {
                 const int buf = gi & 1;
                 const int cbase = ch * CC;
-                k1p_wait(&bar_e_full[buf], (gi >> 1) & 1, s_abort);
+                k1p_wait(&bar_e_full[buf], (gi >> 1) & 1, s_abort, p.tflag);
                 float sum[4] = {0.f, 0.f, 0.f, 0.f};
                 if (dw_active) {
                     const int c0 = cbase + cv * 4;

@@ -562,67 +562,24 @@ __global__ void __launch_bounds__(NT) se_gate_kernel(const float* __restrict__ p
     se_gate_crop<false, NT>(partial + (long long)n * tiles * C, tiles, inv_hw, w1t, b1, w2, b2, gate + (long long)n * C, C, Cse, sm);
 }
 
-// SE gate, CPB crops per CTA: the two FC weight matrices (up to 2 x 221 KB at C=1152) are read once per CTA and reused
-// for all of its crops instead of once per crop (se_gate_kernel re-streams them 512 times from L2 at N=512).
-// Per crop the arithmetic and its order are exactly those of se_gate_crop, so results do not depend on the grouping.
-template <int CPB>
-__global__ void __launch_bounds__(256) se_gate_multi_kernel(const float* __restrict__ partial, int tiles, float inv_hw,
-                                                            const float* __restrict__ w1t, const float* __restrict__ b1,
-                                                            const float* __restrict__ w2, const float* __restrict__ b2,
-                                                            float* __restrict__ gate, int C, int Cse, int ncrops) {
-    extern __shared__ float sm[];            // mean[CPB][C] | hid[CPB][Cse]
-    float* mean = sm;
-    float* hid = sm + CPB * C;
-    const int tid = threadIdx.x;
-    const int crop0 = blockIdx.x * CPB;
-    const int nc = min(CPB, ncrops - crop0);
-    for (int idx = tid; idx < nc * C; idx += 256) {
-        const int q = idx / C, c = idx - q * C;
-        const float* pn = partial + (long long)(crop0 + q) * tiles * C + c;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int t = 0;
-        for (; t + 3 < tiles; t += 4) {
-            const float* p4 = pn + (long long)t * C;
-            s0 += p4[0]; s1 += p4[C]; s2 += p4[2 * C]; s3 += p4[3 * C];
-        }
-        for (; t < tiles; ++t) s0 += pn[(long long)t * C];
-        mean[q * C + c] = ((s0 + s1) + (s2 + s3)) * inv_hw;
-    }
-    __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int j = warp; j < Cse; j += 8) {
-        float acc[CPB];
+// softmax (reference utils.py:7-11: exp(x - max) / sum) and the bin-index expectation (reference whenet.py:31-33) of the
+// three heads: warp w < 3 of the CTA decodes head w from the 252 logits in shared memory.
+__device__ __forceinline__ void decode_heads(const float* logit, float* __restrict__ angles_n, int warp, int lane) {
+    if (warp < 3) {
+        const int off = warp == 0 ? 0 : (warp == 1 ? 120 : 186);
+        const int cnt = warp == 0 ? 120 : 66;
+        float mx = -INFINITY;
+        for (int j = lane; j < cnt; j += 32) mx = fmaxf(mx, logit[off + j]);
 #pragma unroll
-        for (int q = 0; q < CPB; ++q) acc[q] = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const float w = w1t[(long long)j * C + c];
-#pragma unroll
-            for (int q = 0; q < CPB; ++q)
-                if (q < nc) acc[q] = fmaf(mean[q * C + c], w, acc[q]);
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float se = 0.f, sw = 0.f;
+        for (int j = lane; j < cnt; j += 32) {
+            const float e = expf(logit[off + j] - mx);
+            se += e; sw = fmaf(e, (float)j, sw);
         }
 #pragma unroll
-        for (int q = 0; q < CPB; ++q) {
-            float s = acc[q];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0 && q < nc) hid[q * Cse + j] = swish_f(s + b1[j]);
-        }
-    }
-    __syncthreads();
-    for (int c = tid; c < C; c += 256) {
-        float s[CPB];
-        const float bb = b2[c];
-#pragma unroll
-        for (int q = 0; q < CPB; ++q) s[q] = bb;
-        for (int j = 0; j < Cse; ++j) {
-            const float w = w2[(long long)j * C + c];
-#pragma unroll
-            for (int q = 0; q < CPB; ++q)
-                if (q < nc) s[q] = fmaf(hid[q * Cse + j], w, s[q]);
-        }
-#pragma unroll
-        for (int q = 0; q < CPB; ++q)
-            if (q < nc) gate[(long long)(crop0 + q) * C + c] = sigmoid_f(s[q]);
+        for (int o = 16; o > 0; o >>= 1) { se += __shfl_xor_sync(0xffffffffu, se, o); sw += __shfl_xor_sync(0xffffffffu, sw, o); }
+        if (lane == 0) angles_n[warp] = (sw / se) * 3.0f - (warp == 0 ? 180.0f : 99.0f);
     }
 }
 
@@ -665,24 +622,20 @@ __global__ void __launch_bounds__(256) head_pool_fc_decode_kernel(const T* __res
     __syncthreads();
     if (logits_out)
         for (int j = tid; j < NL; j += 256) logits_out[(long long)n * NL + j] = logit[j];
-    if (warp < 3) {
-        // reference utils.py:7-11 then whenet.py:31-33
-        const int off = warp == 0 ? 0 : (warp == 1 ? 120 : 186);
-        const int cnt = warp == 0 ? 120 : 66;
-        float mx = -INFINITY;
-        for (int j = lane; j < cnt; j += 32) mx = fmaxf(mx, logit[off + j]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float se = 0.f, sw = 0.f;
-        for (int j = lane; j < cnt; j += 32) {
-            const float e = expf(logit[off + j] - mx);
-            se += e; sw = fmaf(e, (float)j, sw);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { se += __shfl_xor_sync(0xffffffffu, se, o); sw += __shfl_xor_sync(0xffffffffu, sw, o); }
-        if (lane == 0) angles[(long long)n * 3 + warp] = (sw / se) * 3.0f - (warp == 0 ? 180.0f : 99.0f);
-    }
+    decode_heads(logit, angles + (long long)n * 3, warp, lane);
 }
+
+// decode only (test hook whenet_debug_decode): logits [N][252] -> angles [N][3], the same device function as the head kernel
+__global__ void __launch_bounds__(96) decode_only_kernel(const float* __restrict__ logits, float* __restrict__ angles) {
+    __shared__ float logit[252 + 4];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    for (int j = tid; j < 252; j += 96) logit[j] = logits[(long long)n * 252 + j];
+    __syncthreads();
+    decode_heads(logit, angles + (long long)n * 3, tid >> 5, tid & 31);
+}
+
+// raises the context's timeout flag from the device (test hook: proves every synchronising path reports it)
+__global__ void raise_flag_kernel(int* flag) { *reinterpret_cast<volatile int*>(flag) = 1; }
 
 // T -> float copy for debug taps
 template <typename T>

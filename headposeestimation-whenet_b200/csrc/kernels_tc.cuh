@@ -1,4 +1,4 @@
-// kernels_tc.cuh - tcgen05 (5th-gen tensor core) kernels for the 1x1 convolutions.
+// kernels_tc.cuh - tcgen05 (5th-gen tensor core) kernels for the 1x1 convolutions + the helpers every tcgen05 kernel shares.
 //
 //   out[m, n] = act( bias[n] + sum_k (A[m,k] * gate[m/hw, k]) * Wt[n,k] ) (+ resid[m,n])
 //
@@ -6,20 +6,13 @@
 // Wt : BN-folded weights transposed to [N = Cout][K], 16-bit                           -> "K-major"
 // D  : fp32 accumulator in tensor memory (TMEM), 128 lanes (pixels) x n_tile columns
 //
-// One CTA owns a 128-pixel x n_tile(<=256) output tile.  The K loop runs in
-// blocks of 64 channels through a 2-stage shared-memory ring:
-//   all 128 threads : global -> registers (-> x SE gate) -> st.shared in the canonical
-//                     K-major SWIZZLE_128B UMMA layout (16-byte chunk c of row r lands at
-//                     chunk c ^ (r & 7) of its 128-byte row; 8-row atoms of 1024 B)
-//   thread 0        : tcgen05.mma.cta_group::1.kind::f16 (M=128, N=n_tile, K=16) x 4 per block,
-//                     tcgen05.commit -> mbarrier of that stage (frees the stage for the next fill)
-//   epilogue        : warp w reads TMEM lanes 32w..32w+31 with tcgen05.ld (thread == pixel row),
-//                     adds the folded BN shift, swish / residual, packs to 16 bit, 16-byte stores.
-// Several CTAs are resident per SM (smem <= 96 KB, TMEM <= 256 columns), so one CTA's
-// fills overlap another's MMAs and epilogue.
+// Operands sit in shared memory in the canonical K-major SWIZZLE_128B UMMA layout (16-byte chunk c of row r lands at
+// chunk c ^ (r & 7) of its 128-byte row; 8-row atoms of 1024 B); one elected thread issues
+// tcgen05.mma.cta_group::1.kind::f16 (M=128, N=n_tile, K=16), tcgen05.commit -> mbarrier hands stages back, and the
+// epilogue reads TMEM lanes with tcgen05.ld (thread == pixel row).
 //
-// Every mbarrier wait is bounded: a wait that exceeds its budget sets a flag in
-// global memory and the CTA bails out instead of hanging the GPU.
+// Every mbarrier wait is bounded: a wait that exceeds its budget raises the context's timeout flag (mapped pinned host
+// memory) and the CTA bails out instead of hanging the GPU.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -31,13 +24,12 @@
 namespace whenet {
 namespace tc {
 
-// one copy per translation unit (the library is built from several, see build.py): kernels raise the flag of their own
-// unit and every unit exports a reader (whenet::tu_timeout_*), which the API unit polls after a forward
-static __device__ int g_tc_timeout_flag = 0;
+// Timeout flag: ONE int per context in mapped pinned host memory (whenet_api.cu); every tcgen05 kernel gets its device
+// address as a parameter and raises it when a bounded mbarrier wait expires.  The host reads it straight from the pinned
+// page after any stream synchronisation - no per-translation-unit device symbols, no extra copies.
 
 constexpr int BM = 128;          // pixels per CTA == TMEM lanes == UMMA M
 constexpr int BK = 64;           // channels per stage (one 128-byte swizzle row of 16-bit elements)
-constexpr int STAGES = 2;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -46,7 +38,7 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 // bounded parity wait; returns false on timeout
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* tflag) {
     const uint32_t addr = smem_u32(bar);
     for (uint32_t it = 0; it < (1u << 22); ++it) {
         uint32_t done;
@@ -57,7 +49,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) return true;
     }
-    atomicExch(&g_tc_timeout_flag, 1);
+    *reinterpret_cast<volatile int*>(tflag) = 1;
     return false;
 }
 
@@ -131,209 +123,8 @@ template <> __device__ __forceinline__ uint4 scale8<__half>(uint4 raw, const flo
     return raw;
 }
 
-// grid = (n_tiles, m_tiles): CTAs sharing an A tile are adjacent in launch order (L2 reuse of A).
-template <typename T, bool SWISH, bool GATE, bool RESID>
-__global__ void __launch_bounds__(128) pw_tc_kernel(const T* __restrict__ A, const T* __restrict__ Wt,
-                                                    const float* __restrict__ bias, const float* __restrict__ gate,
-                                                    const T* __restrict__ resid, T* __restrict__ out,
-                                                    long long M, int K, int N, int hw,
-                                                    int n_tile,        // output columns per CTA (multiple of 8)
-                                                    int umma_n,        // n_tile rounded up to 16
-                                                    int tmem_cols,     // power of two >= umma_n, >= 32
-                                                    int n_stages,      // 1 when K <= 64 (single k-block), else 2
-                                                    uint32_t idesc) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t mbar[STAGES];
-    __shared__ uint32_t s_tmem_base;
-    __shared__ int s_abort;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // SWIZZLE_128B atoms need 1024-byte alignment
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int w_stage_bytes = umma_n * BK * 2;
-    uint8_t* sA = smem;                                 // [STAGES][128 rows][128 B]
-    uint8_t* sW = smem + n_stages * A_STAGE_BYTES;      // [n_stages][umma_n rows][128 B]
-
-    const long long m0 = (long long)blockIdx.y * BM;
-    const int n0 = blockIdx.x * n_tile;
-    const int n_valid = min(n_tile, N - n0);            // real output columns of this CTA
-
-    if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
-        s_abort = 0;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"((uint32_t)tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = s_tmem_base;
-
-    const int nkb = (K + BK - 1) / BK;
-    const int kchunks = K >> 3;                          // valid 16-byte chunks per row (K % 8 == 0)
-
-    for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb & 1;
-        if (kb >= STAGES) {
-            // the MMAs that read this stage (block kb-2) must have completed
-            if (!mbar_wait(&mbar[s], ((kb >> 1) - 1) & 1)) s_abort = 1;
-        }
-        uint8_t* a_st = sA + s * A_STAGE_BYTES;
-        uint8_t* w_st = sW + s * w_stage_bytes;
-        const int kc0 = kb * 8;                          // first global chunk of this block
-        // ---- A tile: 128 rows x cb valid 16-byte chunks (cb = 8 except in the last block), flat mapping so no
-        //      thread idles on thin layers; one extra zero chunk when cb is odd (the last k-step reads 2 chunks)
-        {
-            const int cb = min(8, kchunks - kc0);
-            const int cbp = (cb + 1) & ~1;
-            for (int idx = tid; idx < BM * cbp; idx += 128) {
-                const int r = idx / cbp, c = idx - r * cbp;
-                const long long m = m0 + r;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (m < M && c < cb) {
-                    v = *reinterpret_cast<const uint4*>(A + m * K + (long long)(kc0 + c) * 8);
-                    if (GATE) v = scale8<T>(v, gate + (long long)((int)m / hw) * K + (kc0 + c) * 8);   // 32-bit divide (M < 2^31)
-                }
-                *reinterpret_cast<uint4*>(a_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
-            }
-        }
-        // ---- W tile: umma_n rows x 8 chunks (rows >= n_valid and chunks >= K/8 are zero)
-        const int wcb = min(8, kchunks - kc0), wcbp = (wcb + 1) & ~1;
-        for (int idx = tid; idx < umma_n * wcbp; idx += 128) {
-            const int r = idx / wcbp, c = idx - r * wcbp;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (r < n_valid && c < wcb)
-                v = *reinterpret_cast<const uint4*>(Wt + (long long)(n0 + r) * K + (long long)(kc0 + c) * 8);
-            *reinterpret_cast<uint4*>(w_st + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
-        }
-        // generic-proxy writes -> visible to the async proxy (tensor core) before the MMA is issued
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid == 0 && !s_abort) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int krem = min(BK, K - kb * BK);
-            const int ksteps = (krem + 15) >> 4;
-            const uint64_t ad = make_desc(smem_u32(a_st)), bd = make_desc(smem_u32(w_st));
-            for (int k = 0; k < ksteps; ++k)      // +32 bytes along K inside the swizzle row = +2 in the address field
-                umma_f16(tmem_d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-            umma_commit(&mbar[s]);
-        }
-    }
-    // ---- wait for the last MMA group (commits complete in issue order)
-    {
-        const int last = nkb - 1;
-        if (!mbar_wait(&mbar[last & 1], (last >> 1) & 1)) s_abort = 1;
-    }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    __syncthreads();
-
-    // ---- epilogue: thread == pixel row.  TMEM -> registers -> (+shift, swish, +residual) -> 16-bit -> the now idle
-    //      operand stages (row pitch odd in 16-byte units: conflict-free) -> flat, fully coalesced 16-byte global stores
-    const long long m = m0 + tid;
-    const int nch = n_valid >> 3;                        // 16-byte chunks per output row
-    const int pitch16 = nch | 1;
-    uint4* stage = reinterpret_cast<uint4*>(smem);
-    if (!s_abort) {
-        const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);
-        for (int c0 = 0; c0 < n_valid; c0 += 16) {
-            float v[16];
-            tmem_ld16(lane_base + (uint32_t)c0, v);     // warp-collective: every lane executes it
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int n = n0 + c0 + h * 8;
-                if (c0 + h * 8 >= n_valid) break;
-                float o[8];
-                const float4 b0 = *reinterpret_cast<const float4*>(bias + n), b1 = *reinterpret_cast<const float4*>(bias + n + 4);
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float x = v[h * 8 + j] + bb[j];
-                    o[j] = SWISH ? swish_fast(x) : x;
-                }
-                if (RESID && m < M) {
-                    float r[8];
-                    ld8<T>(resid + m * N + n, r);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] += r[j];
-                }
-                st8<T>(reinterpret_cast<T*>(stage + tid * pitch16 + ((c0 >> 3) + h)), o);
-            }
-        }
-    }
-    __syncthreads();
-    if (!s_abort) {
-        const int rows_valid = (int)min((long long)BM, M - m0);
-        for (int idx = tid; idx < rows_valid * nch; idx += 128) {
-            const int r = idx / nch, j = idx - r * nch;
-            *reinterpret_cast<uint4*>(out + (m0 + r) * N + n0 + j * 8) = stage[r * pitch16 + j];
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)tmem_cols) : "memory");
-}
-
-// returns 0 = launched, >0 = shape unsupported (caller falls back to the CUDA-core kernel), <0 = error
-template <typename T>
-int launch_pw_tc(cudaStream_t stream, const T* A, const void* Wt16, const float* bias, const float* gate, const T* resid,
-                 T* out, long long M, int K, int N, int hw, bool swish) {
-    if (sizeof(T) != 2) return 1;
-    if ((K & 7) || (N & 7) || M > 0x7fffffffLL) return 1;
-    // columns per CTA: whole N when it fits 256 TMEM columns, otherwise an even split into <=256 wide tiles;
-    // then split further (A is re-read from L2, cheap) until the grid covers the 148 SMs about twice
-    int n_tile = N;
-    if (N > 256) {
-        int parts = (N + 255) / 256;
-        while (true) {
-            n_tile = ((N + parts - 1) / parts + 15) & ~15;
-            if (n_tile <= 256) break;
-            ++parts;
-        }
-    }
-    {
-        const long long m_tiles = (M + BM - 1) / BM;
-        while (n_tile > 48 && m_tiles * ((N + n_tile - 1) / n_tile) < 296) {
-            const int parts = (N + n_tile - 1) / n_tile + 1;
-            const int nt = ((N + parts - 1) / parts + 15) & ~15;
-            if (nt >= n_tile) break;
-            n_tile = nt;
-        }
-    }
-    const int umma_n = (n_tile + 15) & ~15;
-    int tmem_cols = 32;
-    while (tmem_cols < umma_n) tmem_cols <<= 1;
-    const uint32_t idesc = make_idesc(std::is_same<T, __nv_bfloat16>::value, umma_n);
-    const int n_stages = K > BK ? STAGES : 1;
-    // operand stages, reused afterwards as the output staging tile (128 rows x odd pitch in 16-byte units)
-    const size_t stage_bytes = (size_t)n_stages * (A_STAGE_BYTES + (size_t)umma_n * BK * 2);
-    const size_t out_bytes = (size_t)BM * ((size_t)(n_tile >> 3) | 1) * 16;
-    const size_t smem = (stage_bytes > out_bytes ? stage_bytes : out_bytes) + 1024;
-    dim3 grid((unsigned)((N + n_tile - 1) / n_tile), (unsigned)((M + BM - 1) / BM));
-    const T* W = reinterpret_cast<const T*>(Wt16);
-#define TC(SW, GA, RE)                                                                                              \
-    do {                                                                                                            \
-        auto kfn = pw_tc_kernel<T, SW, GA, RE>;                                                                     \
-        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) return -1; \
-        kfn<<<grid, 128, smem, stream>>>(A, W, bias, gate, resid, out, M, K, N, hw, n_tile, umma_n, tmem_cols, n_stages, idesc); \
-    } while (0)
-    if (swish && !gate && !resid) TC(true, false, false);
-    else if (!swish && gate && !resid) TC(false, true, false);
-    else if (!swish && gate && resid) TC(false, true, true);
-    else if (!swish && !gate && !resid) TC(false, false, false);
-    else if (!swish && !gate && resid) TC(false, false, true);
-    else return 1;
-#undef TC
-    return 0;
-}
-
 // ----------------------------------------------------------------------------- pw_tc2: cp.async ring
-// Same contract as pw_tc_kernel, different data movement:
+// pw_tc2_kernel: one 128-pixel x n_tile(<=256) output tile per CTA, K in blocks of 64 channels:
 //   * operand K blocks travel global -> shared with cp.async (16 B, zero-fill for tails) through a ring of
 //     n_stages stages, several blocks in flight, no register staging;
 //   * the SE gate is applied IN shared memory by the thread that copied the chunk (so no extra barrier):
@@ -390,7 +181,7 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
                                                      int M, int K, int N, int hw,
                                                      int n_tile, int umma_n, int tmem_cols, int n_stages,
                                                      int tiles_per_crop,     // GATE == 2 only
-                                                     uint32_t idesc) {
+                                                     uint32_t idesc, int* tflag) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mbar[4];
     __shared__ uint32_t s_tmem_base;
@@ -559,20 +350,20 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
         // refill the stage block kb-1 used (its MMAs are done or about to be) with block kb-1+n_stages
         if (kb >= 1 && kb - 1 + n_stages < nkb) {
             const int pb = kb - 1;
-            if (!mbar_wait(&mbar[pb % n_stages], (pb / n_stages) & 1)) s_abort = 1;
+            if (!mbar_wait(&mbar[pb % n_stages], (pb / n_stages) & 1, tflag)) s_abort = 1;
             fill(pb + n_stages);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
     {
         const int last = nkb - 1;
-        if (!mbar_wait(&mbar[last % n_stages], (last / n_stages) & 1)) s_abort = 1;
+        if (!mbar_wait(&mbar[last % n_stages], (last / n_stages) & 1, tflag)) s_abort = 1;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();
 
-    // ---- epilogue (as in pw_tc_kernel): TMEM -> +shift, swish, +residual -> 16-bit -> stage -> coalesced stores
+    // ---- epilogue: TMEM -> +shift, swish, +residual -> 16-bit -> stage -> coalesced stores
     const int nch = n_valid >> 3;
     const float inv_nch = 1.0f / (float)(nch > 0 ? nch : 1);
     const int pitch16 = nch | 1;
@@ -620,7 +411,7 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
 }
 
 template <typename T>
-int launch_pw_tc2(cudaStream_t stream, const T* A, const void* Wt16, const float* bias, const float* gate, const T* resid,
+int launch_pw_tc2(cudaStream_t stream, int* tflag, const T* A, const void* Wt16, const float* bias, const float* gate, const T* resid,
                   T* out, long long M, int K, int N, int hw, bool swish, int stage_cap = 0, int smem_budget_kb = 54, int min_ctas = 296) {
     if (sizeof(T) != 2) return 1;
     if ((K & 7) || (N & 7) || M > 0x7fffffffLL) return 1;
@@ -667,7 +458,7 @@ int launch_pw_tc2(cudaStream_t stream, const T* A, const void* Wt16, const float
     do {                                                                                                             \
         auto kfn = pw_tc2_kernel<T, SW, GA, RE>;                                                                     \
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024) != cudaSuccess) return -1; \
-        kfn<<<grid, 128, smem, stream>>>(A, W, bias, gate, resid, out, (int)M, K, N, hw, n_tile, umma_n, tmem_cols, n_stages, tpc, idesc); \
+        kfn<<<grid, 128, smem, stream>>>(A, W, bias, gate, resid, out, (int)M, K, N, hw, n_tile, umma_n, tmem_cols, n_stages, tpc, idesc, tflag); \
     } while (0)
     if (swish && !gate && !resid) TC2(true, 0, false);
     else if (!swish && !gate && !resid) TC2(false, 0, false);
@@ -677,13 +468,6 @@ int launch_pw_tc2(cudaStream_t stream, const T* A, const void* Wt16, const float
     else return 1;
 #undef TC2
     return 0;
-}
-
-static inline int read_and_clear_timeout_flag() {     // internal linkage on purpose: it reads THIS unit's flag
-    int v = 0, z = 0;
-    if (cudaMemcpyFromSymbol(&v, g_tc_timeout_flag, sizeof(int)) != cudaSuccess) return -1;
-    if (v) cudaMemcpyToSymbol(g_tc_timeout_flag, &z, sizeof(int));
-    return v;
 }
 
 }  // namespace tc

@@ -19,9 +19,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_fused.cuh"
-#include "kernels_fused_tc.cuh"
 #include "kernels_crop.cuh"
-#include "kernels_k0.cuh"
 #include "kernels_k1p.cuh"
 
 // The fused-kernel launchers are instantiated in their own translation units (inst_k1_bf16.cu, inst_k1_f16.cu, inst_k1x.cu)
@@ -30,26 +28,11 @@ namespace fused {
 #define WHENET_EXTERN_FUSED(T)                                                                            \
     extern template int launch_k1<T>(cudaStream_t, K1Params, int, int, int, int, size_t, int);            \
     extern template int launch_dw_only<T>(cudaStream_t, K1Params, size_t, int);                           \
-    extern template int launch_k1p<T>(cudaStream_t, K1PParams, int, int, int, size_t, int, int);          \
-    extern template int launch_k1t<T>(cudaStream_t, const K1TParams&, int, int, size_t, int);
+    extern template int launch_k1p<T>(cudaStream_t, K1PParams, int, int, int, size_t, int, int);
 WHENET_EXTERN_FUSED(__nv_bfloat16)
 WHENET_EXTERN_FUSED(__half)
 #undef WHENET_EXTERN_FUSED
 }  // namespace fused
-int tu_timeout_k1_bf16();
-int tu_timeout_k1_f16();
-int tu_timeout_k1x();
-// any tcgen05 kernel of any unit timed out on an mbarrier since the last call (-1: this unit's flag could not be read).
-// A unit whose flag cannot be read is skipped (and the sticky CUDA error cleared) rather than failing every forward.
-static int any_tc_timeout() {
-    int r = tc::read_and_clear_timeout_flag();
-    const int others[3] = {tu_timeout_k1_bf16(), tu_timeout_k1_f16(), tu_timeout_k1x()};
-    for (int x : others) {
-        if (x < 0) cudaGetLastError();
-        else if (x > 0 && r == 0) r = 1;
-    }
-    return r;
-}
 }  // namespace whenet
 
 namespace {
@@ -121,7 +104,6 @@ struct BlockW {   // device pointers into the fp32 arena
 
 struct K1Plan { bool valid = false; whenet::fused::K1Params p{}; int R = 0; int NT = 256; size_t smem = 0; };
 struct K1PPlan { bool valid = false; whenet::fused::K1PParams p{}; int R = 0; size_t smem = 0; };
-struct K1TPlan { bool valid = false; whenet::fused::K1TParams p{}; size_t smem = 0; };
 struct GraphKey {
     int n, in_u8, sig;
     const void* in;
@@ -138,34 +120,31 @@ struct whenet_ctx {
     int device = 0, max_batch = 0, precision = 0;
     int chunk = 0;          // crops per pass through the net
     int use_tc = 0;         // tensor-core kernels for the 1x1 convs
-    bool tc_used = false;   // a tcgen05 kernel ran since the last timeout-flag check
+    int* h_tflag = nullptr; // mbarrier-timeout flag: mapped pinned host memory, raised by any tcgen05 kernel of this context
+    int* d_tflag = nullptr; // ... its device address (kernel parameter)
     int dw_variant = 1;     // 0 = one output per thread, 1 = register-blocked strips
     int pw_stage_cap = 0, pw_smem_kb = 54, pw_min_ctas = 148;    // pw_tc2 ring: max stages (0 = up to 4) and per-CTA smem budget that trades depth for co-residency
-    int pw_variant = 2;     // tensor-core 1x1 kernel: 1 = register-staged 2-stage ring, 2 = cp.async ring + in-smem SE gate
     int stem_variant = 1;   // 0 = 4 threads / pixel straight from global, 1 = smem-tiled, weights in the constant bank
     whenet::StemParams stem_params{};
-    whenet::StemParams stem_params_h{};   // 0.5 * (weights, shift) for K0
-    int use_k0 = 0;                       // stem + block-1 depthwise fused (16-bit modes, uint8 input)
     bool async_host = false;    // set by whenet_forward_u8_async for the duration of the call
     unsigned host_pass_ctr = 0; // staging slot selector, persistent across calls so consecutive calls double-buffer
     float* d_angles_slot[2] = {nullptr, nullptr};
     float* d_logits_slot[2] = {nullptr, nullptr};
     int host_chunk = 1 << 30;   // host inputs can run in passes of at most this many crops so the H2D of pass i+1 hides behind
                                 // pass i; measured on B200 (round 1): whole-batch passes win (45.3k vs 42.1k crops/s at 256)
+    int cfg_epoch = 0;      // bumped by every set_option / plan change: part of the graph cache key
     int use_graph = 0;      // replay device-resident forwards from a captured CUDA graph (small-batch latency)
     std::vector<GraphEntry> graphs;
     int use_fused = 0;      // K1: expand + depthwise in one kernel (16-bit storage only; default on for bf16/fp16)
     int fused_max_block = 16;  // blocks 2..fused_max_block use K1
     std::vector<K1Plan> k1;
-    std::vector<K1TPlan> k1t;
     std::vector<K1PPlan> k1p;  // k1_variant 3: persistent warp-specialised K1 for the blocks with several tiles per crop
     int sm_count = 148;
     int k1p_epi_warps = 8;     // epilogue group of K1P: 4 or 8 warps (the depthwise group gets the other 10 or 6)
     int k1p_min_crops = 8;     // below this a persistent grid cannot fill the SMs: K1 with its chunk split is used instead
     K1Plan dw1;                // block 1 (no expand): depthwise-only instance of K1
     int dw1_fused = 1;
-    int k1_variant = 1;        // 1 = K1 (depthwise on CUDA cores), 2 = K1T (depthwise on the tensor core via diagonal weights)
-    int k1t_max_block = 16;
+    int k1_variant = 1;        // 1 = K1 everywhere, 3 = K1P (persistent, warp-specialised) for the blocks with several tiles per crop
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     bool weights_loaded = false;
     std::vector<BlockCfg> blocks;
@@ -185,8 +164,6 @@ struct whenet_ctx {
     float *d_partial = nullptr, *d_gate = nullptr, *d_angles = nullptr, *d_logits = nullptr, *d_pooled = nullptr;
     int* d_se_counter = nullptr;   // per-crop tickets of the fused SE excite (zero between kernels)
     int se_wide = 0;               // 1024-thread SE gate CTAs also for large batches
-    int se_variant = 0;            // 1 = eight crops per CTA share one pass over the SE weights; measured SLOWER on B200
-                                   // (0.71 vs 0.47 ms per 512 crops: 64 fat CTAs lose to 512 thin ones), kept as an option
     int se_scale_out = 1;          // ... and gate their depthwise output in place, so the project conv runs without a gate pass
     int k1_split_ctas = 120;       // small batches: split a crop's chunks over CTAs until the K1 grid has this many (measured: at 256
                                    // crops per stream the late blocks run faster unsplit, with the SE tail, than split to 296)
@@ -214,6 +191,16 @@ struct whenet_ctx {
 namespace {
 
 size_t esize(int precision) { return precision == WHENET_PRECISION_FP32 ? 4 : 2; }
+
+// The stream has been synchronised: did any tcgen05 kernel of this context give up on an mbarrier?  (plain host read of
+// the mapped pinned flag; the flag is cleared so the context stays usable)
+int check_timeout(whenet_ctx* c) {
+    if (c->h_tflag && *reinterpret_cast<volatile int*>(c->h_tflag)) {
+        *reinterpret_cast<volatile int*>(c->h_tflag) = 0;
+        return fail(WHENET_ECUDA, "a tcgen05 kernel timed out waiting on an mbarrier (results invalid)");
+    }
+    return 0;
+}
 
 // ----------------------------------------------------------------------------- profiling helpers
 struct Scope {
@@ -314,8 +301,8 @@ int ensure_ws(whenet_ctx* c) {
     }
     for (const K1Plan& pl : c->k1)
         if (pl.valid) part = std::max(part, (size_t)pl.p.tiles_x * pl.p.tiles_y * pl.p.Cexp);
-    for (const K1TPlan& pl : c->k1t)
-        if (pl.valid) part = std::max(part, (size_t)pl.p.tiles_x * pl.p.tiles_y * pl.p.Cexp);
+    for (const K1PPlan& pl : c->k1p)          // persistent variant: its own tile shapes (tuning hook) size the partials too
+        if (pl.valid) part = std::max(part, (size_t)pl.p.tiles * pl.p.k.Cexp);
     if (c->dw1.valid) part = std::max(part, (size_t)c->dw1.p.tiles_x * c->dw1.p.tiles_y * c->dw1.p.Cexp);
     c->ws_io = io; c->ws_ex = ex; c->ws_dw = dw; c->ws_part = part;
     CK(cudaMalloc(&c->bufA, ch * io * es));
@@ -341,9 +328,8 @@ int launch_pw(whenet_ctx* c, const char* name, const T* A, const float* W, const
     Scope sc(c, name, bytes, flops);
     if constexpr (sizeof(T) == 2) {
         if (c->use_tc && Wt16) {
-            int rc = c->pw_variant == 2 ? whenet::tc::launch_pw_tc2<T>(c->stream, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish, c->pw_stage_cap, c->pw_smem_kb, c->pw_min_ctas)
-                                        : whenet::tc::launch_pw_tc<T>(c->stream, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish);
-            if (rc == 0) { CK(cudaGetLastError()); c->tc_used = true; return 0; }
+            int rc = whenet::tc::launch_pw_tc2<T>(c->stream, c->d_tflag, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish, c->pw_stage_cap, c->pw_smem_kb, c->pw_min_ctas);
+            if (rc == 0) { CK(cudaGetLastError()); return 0; }
             if (rc < 0) return fail(WHENET_ECUDA, "tensor-core 1x1 launch failed for %s (rc=%d)", name, rc);
             // rc > 0: shape not supported by the tensor-core kernel -> CUDA-core kernel below
         }
@@ -402,22 +388,7 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
     T* oth = (T*)c->bufB;
     T* E = (T*)c->bufE;
     T* D = (T*)c->bufD;
-    bool did_k0 = false;
-    if constexpr (sizeof(T) == 2 && IN_U8) {
-        if (c->use_k0 && !taps) {
-            const BlockW& w1 = c->bw[0];
-            whenet::fused::K0Params p{};
-            p.in = (const uint8_t*)d_in; p.lut = c->lut; p.w_dw = w1.w_dw_h; p.b_dw = w1.b_dw_h; p.out = D; p.partial = c->d_partial;
-            p.w_se1t = w1.w_se1t; p.b_se1 = w1.b_se1; p.w_se2 = w1.w_se2; p.b_se2 = w1.b_se2; p.gate = c->d_gate;
-            p.se_counter = c->se_fused ? c->d_se_counter : nullptr; p.Cse = c->blocks[0].cse;
-            Scope sc(c, "k0.stem_dw1", (double)nb * (kImgElems + 112.0 * 112 * 32 * sizeof(T)),
-                     2.0 * nb * (112.0 * 112 * 27 * 32 + 112.0 * 112 * 9 * 32));
-            whenet::fused::k0_stem_dw_kernel<T><<<dim3(64, nb), 256, 0, c->stream>>>(c->stem_params_h, p);
-            CK(cudaGetLastError());
-            did_k0 = true;
-        }
-    }
-    if (!did_k0) {
+    {
         Scope sc(c, "stem", (double)nb * (kImgElems * (IN_U8 ? 1.0 : 4.0) + 112.0 * 112 * 32 * sizeof(T)),
                  2.0 * nb * 112.0 * 112 * 27 * 32);
         if (c->stem_variant == 0) {
@@ -437,11 +408,10 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
         bool did_k1 = false;
         bool se_in_k1 = false;      // the SE gate came out of the fused kernel's tail (options se_fused / se_tail)
         bool d_gated = false;       // ... and D already carries it
-        if (i == 0 && did_k0) { did_k1 = true; se_in_k1 = c->se_fused != 0; tiles = 64; }      // K0 already produced D, the partials and the gate
         if constexpr (sizeof(T) == 2) {
             if (i == 0 && !did_k1 && c->use_fused && c->dw1_fused && c->dw1.valid) {
                 whenet::fused::K1Params p = c->dw1.p;
-                p.in = cur; p.wt_aug = nullptr; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial;
+                p.in = cur; p.wt_aug = nullptr; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial; p.tflag = c->d_tflag;
                 p.w_se1t = w.w_se1t; p.b_se1 = w.b_se1; p.w_se2 = w.w_se2; p.b_se2 = w.b_se2; p.gate = c->d_gate; p.Cse = b.cse;
                 se_in_k1 = c->se_fused != 0;
                 p.se_counter = se_in_k1 ? c->d_se_counter : nullptr;
@@ -452,34 +422,21 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
                 CK(cudaGetLastError());
                 tiles = p.tiles_x * p.tiles_y;
                 did_k1 = true;
-            } else if (c->use_fused && c->k1_variant == 2 && c->k1t[i].valid && b.idx <= c->k1t_max_block) {
-                whenet::fused::K1TParams p = c->k1t[i].p;
-                p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial;
-                snprintf(nm, sizeof nm, "b%02d.k1", b.idx);
-                Scope sc(c, nm, (double)nb * ((double)b.hin * b.hin * b.cin + (double)b.hout * b.hout * b.cexp) * sizeof(T),
-                         2.0 * nb * ((double)b.hin * b.hin * b.cin * b.cexp + (double)b.hout * b.hout * b.k * b.k * b.cexp));
-                int rc = whenet::fused::launch_k1t<T>(c->stream, p, b.k, b.s, c->k1t[i].smem, nb);
-                if (rc != 0) return fail(WHENET_ECUDA, "K1T launch failed for block %d (rc=%d)", b.idx, rc);
-                CK(cudaGetLastError());
-                c->tc_used = true;
-                tiles = p.tiles_x * p.tiles_y;
-                did_k1 = true;
             } else if (c->use_fused && c->k1_variant == 3 && c->k1p[i].valid && nb >= c->k1p_min_crops && b.idx <= c->fused_max_block) {
                 whenet::fused::K1PParams pp = c->k1p[i].p;
                 whenet::fused::K1Params& p = pp.k;
-                p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial;
+                p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial; p.tflag = c->d_tflag;
                 snprintf(nm, sizeof nm, "b%02d.k1", b.idx);
                 Scope sc(c, nm, (double)nb * ((double)b.hin * b.hin * b.cin + (double)b.hout * b.hout * b.cexp) * sizeof(T),
                          2.0 * nb * ((double)b.hin * b.hin * b.cin * b.cexp + (double)b.hout * b.hout * b.k * b.k * b.cexp));
                 int rc = whenet::fused::launch_k1p<T>(c->stream, pp, b.k, b.s, c->k1p[i].R, c->k1p[i].smem, nb, c->sm_count);
                 if (rc != 0) return fail(WHENET_ECUDA, "K1P launch failed for block %d (rc=%d)", b.idx, rc);
                 CK(cudaGetLastError());
-                c->tc_used = true;
                 tiles = pp.tiles;
                 did_k1 = true;
             } else if (c->use_fused && c->k1[i].valid && b.idx <= c->fused_max_block) {
                 whenet::fused::K1Params p = c->k1[i].p;
-                p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial;
+                p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial; p.tflag = c->d_tflag;
                 p.w_se1t = w.w_se1t; p.b_se1 = w.b_se1; p.w_se2 = w.w_se2; p.b_se2 = w.b_se2; p.gate = c->d_gate; p.Cse = b.cse;
                 se_in_k1 = c->se_fused && p.NB == 1;
                 p.se_counter = se_in_k1 ? c->d_se_counter : nullptr;
@@ -505,7 +462,6 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
                 int rc = whenet::fused::launch_k1<T>(c->stream, p, b.k, b.s, c->k1[i].R, c->k1[i].NT, c->k1[i].smem, nb);
                 if (rc != 0) return fail(WHENET_ECUDA, "K1 launch failed for block %d (rc=%d)", b.idx, rc);
                 CK(cudaGetLastError());
-                c->tc_used = true;
                 tiles = p.tiles_x * p.tiles_y;
                 did_k1 = true;
             }
@@ -528,10 +484,7 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
             Scope sc(c, nm, (double)nb * (tiles + 1) * b.cexp * 4.0, 4.0 * nb * b.cexp * b.cse);
             const float inv_hw = 1.0f / (float)(b.hout * b.hout);
             const size_t se_smem = (b.cexp + b.cse) * sizeof(float);
-            if (c->se_variant == 1 && nb >= 64)
-                whenet::se_gate_multi_kernel<8><<<(nb + 7) / 8, 256, 8 * se_smem, c->stream>>>(
-                    c->d_partial, tiles, inv_hw, w.w_se1t, w.b_se1, w.w_se2, w.b_se2, c->d_gate, b.cexp, b.cse, nb);
-            else if (nb < 64 || c->se_wide)     // 32 warps per crop cut the FC latency chain
+            if (nb < 64 || c->se_wide)     // 32 warps per crop cut the FC latency chain
                 whenet::se_gate_kernel<1024><<<nb, 1024, se_smem, c->stream>>>(
                     c->d_partial, tiles, inv_hw, w.w_se1t, w.b_se1, w.w_se2, w.b_se2, c->d_gate, b.cexp, b.cse);
             else
@@ -572,9 +525,6 @@ void drop_graphs(whenet_ctx* c) {
     c->graphs.clear();
 }
 
-int options_signature(const whenet_ctx* c) {
-    return c->chunk * 1000003 + c->se_tail * 1000 + c->se_scale_out * 2000 + c->k1_split_ctas * 13 + c->pw_min_ctas * 7 + c->pw_smem_kb * 11 + c->se_variant * 5 + c->dw1_fused * 3 + c->k1_variant * 16384 + c->k1t_max_block * 65536 + c->use_k0 * 8192 + c->se_fused * 4096 + c->use_tc * 64 + c->dw_variant * 32 + c->use_fused * 16 + c->stem_variant * 8 + c->pw_variant * 2 + c->fused_max_block * 128;
-}
 
 template <typename T, bool IN_U8>
 int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* angles_out, float* logits_out, int out_is_device) {
@@ -586,13 +536,12 @@ int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* a
     float* d_log = logits_out ? (out_is_device ? logits_out : c->d_logits_slot[oslot]) : nullptr;
     // ---- device-resident forwards can be replayed from a captured graph (66 -> 1 launch; small-batch latency)
     const bool graphable = c->use_graph && in_is_device && out_is_device && !c->prof_on && !c->taps_on;
-    GraphKey key{n, IN_U8 ? 1 : 0, options_signature(c), in, d_ang, d_log};
+    GraphKey key{n, IN_U8 ? 1 : 0, c->cfg_epoch, in, d_ang, d_log};
     if (graphable) {
         for (auto& g : c->graphs)
             if (g.key == key) {
                 CK(cudaGraphLaunch(g.exec, c->stream));
                 c->launches += g.launches;
-                c->tc_used = true;
                 return 0;
             }
         CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
@@ -642,7 +591,10 @@ int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* a
             if (logits_out)
                 CK(cudaMemcpyAsync(logits_out, d_log, (size_t)n * WHENET_N_LOGITS * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
             if (in_is_device) c->host_pass_ctr++;
-            if (!c->async_host) CK(cudaStreamSynchronize(c->stream));
+            if (!c->async_host) {
+                CK(cudaStreamSynchronize(c->stream));
+                return check_timeout(c);
+            }
         }
         return 0;
     }
@@ -690,11 +642,7 @@ int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* a
         if (in_is_device) c->host_pass_ctr++;            // keep alternating result buffers for device-in / host-out calls too
         if (c->async_host) return 0;                     // the caller synchronises (whenet_synchronize) before reading
         CK(cudaStreamSynchronize(c->stream));
-        if (c->tc_used) {
-            c->tc_used = false;
-            if (whenet::any_tc_timeout() != 0)
-                return fail(WHENET_ECUDA, "a tcgen05 kernel timed out waiting on an mbarrier (results invalid)");
-        }
+        return check_timeout(c);
     }
     return 0;
 }
@@ -792,7 +740,6 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
     c->blocks = make_blocks();
     c->bw.resize(c->blocks.size());
     c->k1.resize(c->blocks.size());
-    c->k1t.resize(c->blocks.size());
     c->k1p.resize(c->blocks.size());
     if (precision != WHENET_PRECISION_FP32) {
         const BlockCfg& b1 = c->blocks[0];
@@ -815,9 +762,6 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
                                                    pl.p.TH, pl.p.TW, pl.R, pl.p.CC, c->k1p_epi_warps, &pq.p, &pq.smem);
                 pq.R = pl.R;
             }
-            K1TPlan& pt = c->k1t[i];
-            pt.valid = whenet::fused::plan_k1t(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, precision == WHENET_PRECISION_BF16,
-                                               &pt.p, &pt.smem);
         }
     c->use_fused = precision != WHENET_PRECISION_FP32;
     if (const char* e3 = getenv("WHENET_FUSED")) c->use_fused = atoi(e3) && precision != WHENET_PRECISION_FP32;
@@ -834,6 +778,9 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
         CK(cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
     }
+    CK(cudaHostAlloc((void**)&c->h_tflag, sizeof(int), cudaHostAllocMapped));
+    *c->h_tflag = 0;
+    CK(cudaHostGetDevicePointer((void**)&c->d_tflag, c->h_tflag, 0));
     CK(cudaMalloc(&c->d_angles, (size_t)max_batch * 3 * sizeof(float) * 2));
     CK(cudaMalloc(&c->d_logits, (size_t)max_batch * WHENET_N_LOGITS * sizeof(float) * 2));
     for (int i = 0; i < 2; ++i) {
@@ -903,8 +850,6 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
         o_wstem = put(w); o_bstem = put(b); o_lut = put(lut);
         memcpy(c->stem_params.w, w.data(), sizeof(c->stem_params.w));
         memcpy(c->stem_params.b, b.data(), sizeof(c->stem_params.b));
-        for (int i = 0; i < 27 * 32; ++i) c->stem_params_h.w[i] = 0.5f * w[i];
-        for (int i = 0; i < 32; ++i) c->stem_params_h.b[i] = 0.5f * b[i];
     }
     // ---- 16 MBConv blocks
     for (size_t i = 0; i < c->blocks.size(); ++i) {
@@ -1085,12 +1030,7 @@ int whenet_synchronize(whenet_ctx* c) {
     if (!c) return fail(WHENET_EINVAL, "null context");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
-    if (c->tc_used) {
-        c->tc_used = false;
-        if (whenet::any_tc_timeout() != 0)
-            return fail(WHENET_ECUDA, "a tcgen05 kernel timed out waiting on an mbarrier (results invalid)");
-    }
-    return 0;
+    return check_timeout(c);
 }
 
 void* whenet_host_alloc(size_t bytes) {
@@ -1155,18 +1095,16 @@ int debug_conv_impl(whenet_ctx* c, int use_tc, const float* A, const float* W, c
     if (use_tc) {
         rc = 1;
         if constexpr (sizeof(T) == 2)
-            rc = use_tc == 2 ? whenet::tc::launch_pw_tc2<T>(c->stream, dA, dWt, dB, dG, dR, dO, M, K, N, hw, swish != 0)
-                             : whenet::tc::launch_pw_tc<T>(c->stream, dA, dWt, dB, dG, dR, dO, M, K, N, hw, swish != 0);
+            rc = whenet::tc::launch_pw_tc2<T>(c->stream, c->d_tflag, dA, dWt, dB, dG, dR, dO, M, K, N, hw, swish != 0);
         if (rc == 0 && cudaGetLastError() != cudaSuccess) rc = -1;
         if (rc != 0) rc = fail(WHENET_EINVAL, "tensor-core family cannot run M=%lld K=%d N=%d (rc=%d)", M, K, N, rc);
-        else c->tc_used = true;
     } else {
         rc = launch_pw<T>(c, "debug.conv1x1", dA, dW, nullptr, dB, dG, dR, dO, M, K, N, hw, swish != 0);
     }
     c->use_tc = saved;
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (rc == 0 && e != cudaSuccess) rc = fail(WHENET_ECUDA, "debug conv failed: %s", cudaGetErrorString(e));
-    if (rc == 0 && use_tc && whenet::any_tc_timeout() != 0) rc = fail(WHENET_ECUDA, "tcgen05 kernel timed out on an mbarrier");
+    if (rc == 0 && use_tc) rc = check_timeout(c);
     if (rc == 0) {
         e = cudaMemcpy(hO.data(), dO, hO.size() * sizeof(T), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = fail(WHENET_ECUDA, "copy back failed: %s", cudaGetErrorString(e));
@@ -1191,6 +1129,29 @@ int whenet_debug_conv1x1(whenet_ctx* c, int use_tc, const float* A, const float*
     return fail(WHENET_EINVAL, "bad precision");
 }
 
+int whenet_debug_decode(whenet_ctx* c, const float* logits_host, int n, float* angles_host) {
+    if (!c || !logits_host || !angles_host || n < 1) return fail(WHENET_EINVAL, "bad arguments");
+    CK(cudaSetDevice(c->device));
+    float *dl = nullptr, *da = nullptr;
+    CK(cudaMalloc(&dl, (size_t)n * WHENET_N_LOGITS * sizeof(float)));
+    if (cudaMalloc(&da, (size_t)n * 3 * sizeof(float)) != cudaSuccess) { cudaFree(dl); return fail(WHENET_ECUDA, "cudaMalloc failed"); }
+    cudaMemcpyAsync(dl, logits_host, (size_t)n * WHENET_N_LOGITS * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+    whenet::decode_only_kernel<<<n, 96, 0, c->stream>>>(dl, da);
+    cudaMemcpyAsync(angles_host, da, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    const cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(dl); cudaFree(da);
+    if (e != cudaSuccess) return fail(WHENET_ECUDA, "decode failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int whenet_debug_raise_timeout(whenet_ctx* c) {
+    if (!c) return fail(WHENET_EINVAL, "null context");
+    CK(cudaSetDevice(c->device));
+    whenet::raise_flag_kernel<<<1, 1, 0, c->stream>>>(c->d_tflag);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int whenet_debug_set_k1_plan(whenet_ctx* c, int block, int th, int tw, int r, int cc, int nt, int nb) {
     if (!c || block < 2 || block > (int)c->blocks.size()) return fail(WHENET_EINVAL, "bad block index");
     if (c->precision == WHENET_PRECISION_FP32) return fail(WHENET_EINVAL, "K1 needs a 16-bit storage mode");
@@ -1206,6 +1167,7 @@ int whenet_debug_set_k1_plan(whenet_ctx* c, int block, int th, int tw, int r, in
     pl.R = r;
     pl.NT = nt;
     c->k1[block - 1] = pl;
+    c->cfg_epoch++;
     free_ws(c);      // the squeeze-partials buffer depends on the tile count
     return 0;
 }
@@ -1222,6 +1184,7 @@ int whenet_debug_set_k1p_plan(whenet_ctx* c, int block, int th, int tw, int r, i
     if (!pq.valid) return fail(WHENET_EINVAL, "K1P plan %dx%d r%d cc%d epi%d does not fit block %d", th, tw, r, cc, epi_warps, block);
     pq.R = r;
     c->k1p[block - 1] = pq;
+    c->cfg_epoch++;
     free_ws(c);      // the squeeze-partials buffer depends on the tile count
     return 0;
 }
@@ -1260,6 +1223,8 @@ int64_t whenet_launch_count(whenet_ctx* c) { return c ? c->launches : 0; }
 
 int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!c || !key) return fail(WHENET_EINVAL, "bad arguments");
+    drop_graphs(c);        // every option may change the launch sequence a captured graph froze
+    c->cfg_epoch++;
     if (!strcmp(key, "tensor_cores")) { c->use_tc = value && c->precision != WHENET_PRECISION_FP32; return 0; }
     if (!strcmp(key, "streams")) { c->n_streams = value < 1 ? 1 : (value > 4 ? 4 : value); return 0; }
     if (!strcmp(key, "se_fused")) { c->se_fused = value; return 0; }
@@ -1270,6 +1235,7 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!strcmp(key, "k1p_epi_warps")) {
         if (value != 4 && value != 8) return fail(WHENET_EINVAL, "k1p_epi_warps is 4 or 8");
         c->k1p_epi_warps = value;
+        free_ws(c);                                             // the squeeze-partials buffer follows the K1P plans
         for (size_t i = 0; i < c->blocks.size(); ++i) {       // re-plan: the strip-lane count depends on the group sizes
             const BlockCfg& b = c->blocks[i];
             const K1Plan& pl = c->k1[i];
@@ -1283,17 +1249,13 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
         }
         return 0;
     }
-    if (!strcmp(key, "se_variant")) { c->se_variant = value; return 0; }
     if (!strcmp(key, "se_wide")) { c->se_wide = value; return 0; }
-    if (!strcmp(key, "k0")) { c->use_k0 = value && c->precision != WHENET_PRECISION_FP32; return 0; }
     if (!strcmp(key, "host_chunk")) { if (value < 1) return fail(WHENET_EINVAL, "host_chunk must be >= 1"); c->host_chunk = value; return 0; }
     if (!strcmp(key, "graph")) { c->use_graph = value; if (!value) drop_graphs(c); return 0; }
     if (!strcmp(key, "dw_variant")) { c->dw_variant = value; return 0; }
     if (!strcmp(key, "stem_variant")) { c->stem_variant = value; return 0; }
-    if (!strcmp(key, "pw_variant")) { c->pw_variant = value; return 0; }
     if (!strcmp(key, "k1_variant")) { c->k1_variant = value; return 0; }
     if (!strcmp(key, "dw1_fused")) { c->dw1_fused = value; return 0; }
-    if (!strcmp(key, "k1t_max_block")) { c->k1t_max_block = value; return 0; }
     if (!strcmp(key, "pw_stage_cap")) { c->pw_stage_cap = value; return 0; }
     if (!strcmp(key, "pw_smem_kb")) { c->pw_smem_kb = value; return 0; }
     if (!strcmp(key, "pw_min_ctas")) { c->pw_min_ctas = value; return 0; }
@@ -1322,6 +1284,7 @@ void whenet_destroy(whenet_ctx* c) {
     if (c->d_arena16) cudaFree(c->d_arena16);
     if (c->d_angles) cudaFree(c->d_angles);
     if (c->d_logits) cudaFree(c->d_logits);
+    if (c->h_tflag) cudaFreeHost(c->h_tflag);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_ready[i]) cudaEventDestroy(c->ev_ready[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);

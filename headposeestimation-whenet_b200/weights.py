@@ -11,8 +11,8 @@ import numpy as np
 
 from . import arch, h5lite, stlite
 
-DEFAULT_NPZ = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                           "tests", "golden", "whenet_weights.npz")
+# the reference's WHENet.h5 tensors (bit for bit, converted by tools/convert_weights.py): ships inside the package
+DEFAULT_NPZ = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "whenet_weights.npz")
 
 
 def load_snapshot(snapshot) -> Tuple[List[str], Dict[str, np.ndarray]]:

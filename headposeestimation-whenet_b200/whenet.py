@@ -245,6 +245,17 @@ class WHENet:
                                            _ptr(out), M, K, N, int(hw or M), int(swish)))
         return out
 
+    def debug_decode(self, logits) -> np.ndarray:
+        """(N,252) float32 logits -> (N,3) angles through the device decode (reference utils.py:7-11, whenet.py:31-33)."""
+        logits = np.ascontiguousarray(logits, np.float32)
+        out = np.empty((logits.shape[0], 3), np.float32)
+        check(self._L.whenet_debug_decode(self._h, _ptr(logits), logits.shape[0], _ptr(out)))
+        return out
+
+    def debug_raise_timeout(self):
+        """Test hook: a device kernel raises the mbarrier-timeout flag; the next synchronising call must fail."""
+        check(self._L.whenet_debug_raise_timeout(self._h))
+
     def set_k1_plan(self, block: int, th: int, tw: int, r: int, cc: int, nt: int = 256, nb: int = 1) -> bool:
         """Tuning hook (see whenet_debug_set_k1_plan); returns False when the plan cannot run."""
         return self._L.whenet_debug_set_k1_plan(self._h, block, th, tw, r, cc, nt, nb) == 0

@@ -139,6 +139,14 @@ int whenet_debug_conv1x1(whenet_ctx* ctx, int use_tc, const float* A, const floa
  * per CTA (2 only where one tile is the whole image).  WHENET_EINVAL if the plan cannot run. */
 int whenet_debug_set_k1_plan(whenet_ctx* ctx, int block, int th, int tw, int r, int cc, int nt, int nb);
 
+/* Decode only: n x 252 host logits -> n x 3 host angles through the SAME device function the head kernel uses
+ * (softmax of reference utils.py:7-11, expectation of whenet.py:31-33).  Synchronous. */
+int whenet_debug_decode(whenet_ctx* ctx, const float* logits_host, int n, float* angles_host);
+
+/* A device kernel raises the context's mbarrier-timeout flag (what a tcgen05 kernel does when a bounded wait expires):
+ * the next synchronising call (host-output forward, whenet_synchronize) must return WHENET_ECUDA. */
+int whenet_debug_raise_timeout(whenet_ctx* ctx);
+
 /* Same for K1P (option "k1_variant" = 3; blocks with several tiles per crop): tile, strip and chunk shape plus the
  * size of the TMEM-epilogue warp group (4 or 8; the depthwise group gets the remaining warps of the 512-thread CTA). */
 int whenet_debug_set_k1p_plan(whenet_ctx* ctx, int block, int th, int tw, int r, int cc, int epi_warps);

@@ -11,7 +11,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 GOLD = os.path.join(ROOT, "tests", "golden")
-SNAP = os.path.join(GOLD, "whenet_weights.npz")
+SNAP = os.path.join(ROOT, "headposeestimation-whenet_b200", "data", "whenet_weights.npz")
 
 
 def pytest_configure(config):

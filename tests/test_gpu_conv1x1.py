@@ -34,7 +34,7 @@ def net():
     m.close()
 
 
-@pytest.mark.parametrize("use_tc", [0, 1, 2])
+@pytest.mark.parametrize("use_tc", [0, 2])
 @pytest.mark.parametrize("K,N,kind", _layer_shapes())
 def test_conv1x1_shapes(net, use_tc, K, N, kind):
     rng = np.random.default_rng(K * 1000 + N)
@@ -96,12 +96,12 @@ def test_conv1x1_tc_row_tails(net, M):
     W = _bf16_round(rng.standard_normal((K, N)) / np.sqrt(K))
     bias = np.zeros(N, np.float32)
     b = net.debug_conv1x1(A, W, bias, use_tc=0)
-    for fam in (1, 2):
+    for fam in (2,):
         a = net.debug_conv1x1(A, W, bias, use_tc=fam)
         assert np.abs(a - b).max() <= 2.0 ** -6 * max(1.0, np.abs(b).max())
 
 
-@pytest.mark.parametrize("use_tc", [0, 1, 2])
+@pytest.mark.parametrize("use_tc", [0, 2])
 @pytest.mark.parametrize("K,N", [(480, 80), (1152, 192)])
 def test_conv1x1_residual_without_gate(net, use_tc, K, N):
     """Project conv of a block whose depthwise output was already gated by K1's tail: bias + residual, no gate."""

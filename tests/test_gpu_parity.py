@@ -150,33 +150,6 @@ def test_fused_k1_taps(prec, oracle32, sample_crops):
     m.close()
 
 
-@pytest.mark.parametrize("prec", ["bf16", "fp16"])
-def test_fused_k1t_tensor_core_depthwise(prec, oracle32, sample_crops):
-    """K1T: the depthwise runs on the tensor core too (shifted views of the expanded tile x diagonal weight matrices);
-    every depthwise output, SE gate and block output against the oracle."""
-    import whenet_b200
-    m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=8)
-    m.set_option("fused", 1)
-    m.set_option("k1_variant", 2)
-    taps = {}
-    oracle32.get_angle(sample_crops, taps)
-    m.enable_taps(True)
-    got = np.stack(m.get_angle(sample_crops), axis=1)
-    lim = 0.12 if prec == "bf16" else 0.02
-    for i in range(1, 17):
-        for kind in ("dw", "gate", "block"):
-            nm = "%s%d" % (kind, i)
-            ref = taps[nm].astype(np.float64).reshape(-1)
-            g = m.tap(nm).astype(np.float64)
-            e = float(np.sqrt(((g - ref) ** 2).mean()) / (np.sqrt((ref ** 2).mean()) + 1e-30))
-            assert e < lim, (nm, e)
-    ref_ang = np.stack(oracle32.get_angle(sample_crops), axis=1)
-    assert np.abs(got - ref_ang).max() < (1.5 if prec == "bf16" else 0.15)
-    one = np.stack(m.get_angle(sample_crops[1:2]), axis=1)
-    assert np.array_equal(one[0], got[1])
-    m.close()
-
-
 K1_PLAN_SETS = {
     # 512-thread CTAs (one per SM) on the late blocks
     "nt512": {7: (14, 14, 7, 96, 512, 1), 8: (14, 14, 7, 96, 512, 1), 9: (14, 14, 7, 96, 512, 1), 10: (14, 14, 7, 96, 512, 1),
@@ -457,26 +430,6 @@ def test_errors(net32):
 def test_empty_batch(net32):
     y, p, r = net32.get_angle(np.zeros((0, 224, 224, 3), np.uint8))
     assert y.shape == (0,) and y.dtype == np.float32
-
-
-@pytest.mark.parametrize("prec", ["bf16", "fp16"])
-def test_k0_stem_dw1_fusion(prec, sample_crops, jitter_crops, golden):
-    """K0 (stem + block-1 depthwise + SE in one kernel, stem output kept in shared memory) against the unfused path
-    and the oracle; and it must stay batch invariant."""
-    import whenet_b200
-    crops = np.concatenate([sample_crops, jitter_crops])
-    ref = np.array([[s["yaw"], s["pitch"], s["roll"]] for s in golden["samples"]] +
-                   list(zip(golden["jitter"]["yaw"], golden["jitter"]["pitch"], golden["jitter"]["roll"])))
-    m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=16)
-    base = np.stack(m.get_angle(crops), axis=1)
-    m.set_option("k0", 1)
-    got = np.stack(m.get_angle(crops), axis=1)
-    tol = 1.5 if prec == "bf16" else 0.15
-    assert np.abs(got - ref).max() <= tol
-    assert np.abs(got - base).max() <= (0.6 if prec == "bf16" else 0.08)
-    one = np.stack(m.get_angle(crops[5:6]), axis=1)
-    assert np.array_equal(one[0], got[5])
-    m.close()
 
 
 def test_cuda_graph_replay(sample_crops, jitter_crops):

@@ -6,7 +6,7 @@ tensors bit-for-bit under their original names plus ``__layer_names__`` (the
 file's graph-order attribute).  No folding, no re-layout: the CUDA library and
 the oracle both start from the same raw tensors.
 
-    python tools/convert_weights.py /root/reference/WHENet.h5 tests/golden/whenet_weights.npz
+    python tools/convert_weights.py /root/reference/WHENet.h5 headposeestimation-whenet_b200/data/whenet_weights.npz
 """
 import os
 import sys

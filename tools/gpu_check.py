@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
 import whenet_b200
 from whenet_oracle import load_oracle
-GOLD = os.path.join(ROOT, "tests", "golden"); SNAP = os.path.join(GOLD, "whenet_weights.npz")
+GOLD = os.path.join(ROOT, "tests", "golden"); SNAP = os.path.join(ROOT, "headposeestimation-whenet_b200", "data", "whenet_weights.npz")
 crops = np.load(os.path.join(GOLD, "sample_crops.npy"))
 o = load_oracle(SNAP, np.float32); taps = {}
 ref = np.stack(o.get_angle(crops, taps), axis=1)
