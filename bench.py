@@ -32,6 +32,7 @@ import numpy as np  # noqa: E402
 ALGO_ELEMS_PER_CROP = 6_938_112      # activation elements moved by the <=2-kernels-per-block plan
 FLOP_PER_CROP = 2 * 389_533_088
 IMG_BYTES = 224 * 224 * 3
+METRIC = "head-crops/sec @224x224 bf16"   # BASELINE.json's metric; BOTH arms print this exact string (dtype says what ran)
 
 
 def peaks():
@@ -144,7 +145,8 @@ def run_reference(args):
             "config": {"workload": "batch=%d synthetic 224x224x3 uint8 crops per GPU (configs[2]); CPU arm times a %d-crop "
                                    "sample per step" % (args.batch, sample)},
             "cpu_baseline": {"value": v, "unit": "crops/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "%d crops/step x %d steps, torch-CPU fp32 port of the oracle (Keras/TF-1.12 not installable)" % (sample, args.steps)},
+                             "sample": "%d crops/step x %d steps, torch-CPU fp32 port of the oracle (Keras/TF-1.12 not installable); thread probe crops/s %s"
+                                       % (sample, args.steps, getattr(port, "thread_probe", {}))},
             "e2e": {"value": v, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -235,6 +237,7 @@ def main():
         step(W + i)
     e1.record(stream)
     sync_all()
+    net.synchronize()          # also surfaces a tcgen05 mbarrier timeout of any kernel of the timed loop (raises)
     ms = e0.elapsed_time(e1)
     launches = net.launch_count() - l0
     clocks = sampler.finish() if sampler else None
@@ -274,10 +277,27 @@ def main():
         e2e_step(i)
     e1.record(stream)
     sync_all()
+    net.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * KE / (float(t.item()) * 1e-3)
+
+    # ---- e2e through the reference's own call: WHENet.get_angle(np.ndarray) with a PAGEABLE uint8 array (what
+    #      demo.py:12-14 / demo_video.py:24-28 pass), synchronous, wall clock, returns three fresh numpy arrays
+    np_in = [h.numpy().copy() for h in h_in]
+    for i in range(2):
+        net.get_angle(np_in[i & 1])
+    sync_all()
+    KG = max(4, K // 4)
+    t0 = time.perf_counter()
+    for i in range(KG):
+        net.get_angle(np_in[i & 1])
+    dt_ga = time.perf_counter() - t0
+    tg = torch.tensor([dt_ga], device="cuda")
+    if world > 1:
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+    e2e_get_angle = world * B * KG / float(tg.item())
 
     # ---- per-kernel CUDA-event profile (recorded inside the library on the launching stream)
     # the per-kernel table is taken with the two half-batch streams serialised (streams=1): with both streams active
@@ -342,7 +362,7 @@ def main():
             cpu = {"value": sample / dt, "unit": "crops/s", "cores": _t.get_num_threads(), "kind": "port",
                    "sample": "%d crops, median of 3, best thread count of a probe over {all,64,32,16,8}, torch-CPU fp32 port of the oracle with the reference's batch_size=8 chunking "
                              "(Keras/TF-1.12 not installable)" % sample}
-        line = {"metric": "head-crops/sec @224x224 %s" % args.precision, "value": value, "unit": "crops/s", "n_gpus": world,
+        line = {"metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": "batch=%d synthetic 224x224x3 uint8 crops per GPU (BASELINE configs[2]; global batch %d%s)"
@@ -351,7 +371,9 @@ def main():
                            "l2": "inputs rotate over %d resident batches (%d MB > 126 MB L2)" % (NBUF, NBUF * B * IMG_BYTES >> 20)},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": B * IMG_BYTES, "d2h_bytes_per_step": B * 12,
-                        "api": "WHENet.forward_host_to_device + D2H of the angles, two steps in flight (pinned uint8 in, pinned angles out)"},
+                        "api": "WHENet.forward_host_to_device + D2H of the angles, two steps in flight (pinned uint8 in, pinned angles out)",
+                        "get_angle_value": e2e_get_angle,
+                        "get_angle_api": "WHENet.get_angle(np.ndarray): pageable uint8 in, synchronous, numpy out (reference whenet.py:22-34 call shape), wall clock"},
                 "gpu_launches": int(launches * world),
                 "self_check_max_deg_vs_simt_path": self_check,
                 "roofline": roof, "cpu_baseline": cpu}

@@ -91,6 +91,12 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+// two IEEE fp32 FMAs in one instruction (FFMA2): d.x = a.x*b.x + d.x, d.y = a.y*b.y + d.y
+__device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(reinterpret_cast<unsigned long long&>(d))
+        : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+}
 template <typename T> __device__ __forceinline__ void unpack2(uint32_t u, float& lo, float& hi);
 template <> __device__ __forceinline__ void unpack2<__nv_bfloat16>(uint32_t u, float& lo, float& hi) {
     lo = __uint_as_float(u << 16);
@@ -360,32 +366,33 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(con
             const uint32_t e_cv = sE + (uint32_t)(jc * p.e_rows) * pitchE + (uint32_t)cv * 8;
             for (int sidx = pl; sidx < nstrips; sidx += p.PYc) {
                 const int oyl = sidx >> p.spr_log2, oxl0 = (sidx - (oyl << p.spr_log2)) * R;
-                float acc[R][4];
+                float2 acc[R][2];      // (ch0,ch1), (ch2,ch3): one FFMA2 (fma.rn.f32x2) per pair - same IEEE FMAs, half the issue slots
 #pragma unroll
-                for (int r = 0; r < R; ++r) { acc[r][0] = bq.x; acc[r][1] = bq.y; acc[r][2] = bq.z; acc[r][3] = bq.w; }
+                for (int r = 0; r < R; ++r) { acc[r][0] = make_float2(bq.x, bq.y); acc[r][1] = make_float2(bq.z, bq.w); }
                 uint32_t erow = e_cv + (uint32_t)(oyl * S) * e_rowstride + (uint32_t)(oxl0 * S) * pitchE;
 #pragma unroll
                 for (int ky = 0; ky < KS; ++ky) {
-                    float4 wr[KS];
+                    float2 wr[KS][2];
 #pragma unroll
-                    for (int kx = 0; kx < KS; ++kx) wr[kx] = lds_f4(cst + (uint32_t)((1 + ky * KS + kx) * CC) * 4);
+                    for (int kx = 0; kx < KS; ++kx) {
+                        const float4 wq = lds_f4(cst + (uint32_t)((1 + ky * KS + kx) * CC) * 4);
+                        wr[kx][0] = make_float2(wq.x, wq.y); wr[kx][1] = make_float2(wq.z, wq.w);
+                    }
                     uint32_t ea = erow;
 #pragma unroll
                     for (int col = 0; col < NCOL; ++col) {
                         uint32_t a, b;
                         lds64(ea, a, b);
                         ea += pitchE;
-                        float x0, x1, x2, x3;
-                        unpack2<T>(a, x0, x1);
-                        unpack2<T>(b, x2, x3);
+                        float2 x01, x23;
+                        unpack2<T>(a, x01.x, x01.y);
+                        unpack2<T>(b, x23.x, x23.y);
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
                             const int kx = col - r * S;          // compile-time after unrolling
                             if (kx >= 0 && kx < KS) {
-                                acc[r][0] = fmaf(x0, wr[kx].x, acc[r][0]);
-                                acc[r][1] = fmaf(x1, wr[kx].y, acc[r][1]);
-                                acc[r][2] = fmaf(x2, wr[kx].z, acc[r][2]);
-                                acc[r][3] = fmaf(x3, wr[kx].w, acc[r][3]);
+                                ffma2(acc[r][0], x01, wr[kx][0]);
+                                ffma2(acc[r][1], x23, wr[kx][1]);
                             }
                         }
                     }
@@ -397,10 +404,13 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(con
                 for (int r = 0; r < R; ++r) {
                     if (oxl0 + r < p.TW && oy < p.Ho && tx0 + oxl0 + r < p.Ho) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) { acc[r][i] = swish_from_half(acc[r][i]); sum[i] += acc[r][i]; }
+                        for (int i = 0; i < 2; ++i) {
+                            acc[r][i].x = swish_from_half(acc[r][i].x); acc[r][i].y = swish_from_half(acc[r][i].y);
+                            sum[2 * i] += acc[r][i].x; sum[2 * i + 1] += acc[r][i].y;
+                        }
                         uint2 o;
-                        o.x = pack2<T>(acc[r][0], acc[r][1]);
-                        o.y = pack2<T>(acc[r][2], acc[r][3]);
+                        o.x = pack2<T>(acc[r][0].x, acc[r][0].y);
+                        o.y = pack2<T>(acc[r][1].x, acc[r][1].y);
                         *reinterpret_cast<uint2*>(dst + (long long)r * p.Cexp) = o;
                     }
                 }

@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(256) head_pool_fc_decode_kernel(const T* __res
 }
 
 // decode only (test hook whenet_debug_decode): logits [N][252] -> angles [N][3], the same device function as the head kernel
-__global__ void __launch_bounds__(96) decode_only_kernel(const float* __restrict__ logits, float* __restrict__ angles) {
+static __global__ void __launch_bounds__(96) decode_only_kernel(const float* __restrict__ logits, float* __restrict__ angles) {
     __shared__ float logit[252 + 4];
     const int n = blockIdx.x, tid = threadIdx.x;
     for (int j = tid; j < 252; j += 96) logit[j] = logits[(long long)n * 252 + j];
@@ -635,7 +635,7 @@ __global__ void __launch_bounds__(96) decode_only_kernel(const float* __restrict
 }
 
 // raises the context's timeout flag from the device (test hook: proves every synchronising path reports it)
-__global__ void raise_flag_kernel(int* flag) { *reinterpret_cast<volatile int*>(flag) = 1; }
+static __global__ void raise_flag_kernel(int* flag) { *reinterpret_cast<volatile int*>(flag) = 1; }
 
 // T -> float copy for debug taps
 template <typename T>

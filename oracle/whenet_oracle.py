@@ -52,7 +52,13 @@ DW_STRIDE2 = {2, 4, 6, 12}     # EfficientNet-B0: first block of stages 2,3,4,6
 
 
 # ----------------------------------------------------------------------------- primitives
-def _same_pad(n_in: int, k: int, s: int) -> Tuple[int, int, int]:
+def _same_pad(n_in: int, k: int, s: int, symmetric: bool = False) -> Tuple[int, int, int]:
+    """(n_out, pad_before, pad_after).  Default: TensorFlow 'SAME' (out = ceil(in/s), the odd pad element goes AFTER).
+    ``symmetric`` = the PyTorch-style (k-1)//2 on both sides: the WRONG rule for this network, kept only so the tests
+    can prove that the padding convention matters (16.6 deg on the Sample crops)."""
+    if symmetric:
+        p = (k - 1) // 2
+        return (n_in + 2 * p - k) // s + 1, p, p
     n_out = -(-n_in // s)
     total = max((n_out - 1) * s + k - n_in, 0)
     return n_out, total // 2, total - total // 2
@@ -67,14 +73,14 @@ def swish(x):
     return x * _sigmoid(x)
 
 
-def conv2d_same(x: np.ndarray, w: np.ndarray, stride: int) -> np.ndarray:
+def conv2d_same(x: np.ndarray, w: np.ndarray, stride: int, symmetric_pad: bool = False) -> np.ndarray:
     """NHWC conv with HWIO kernel, TF 'SAME' padding, no bias."""
     n, h, wd, cin = x.shape
     kh, kw, _ci, cout = w.shape
     if kh == 1 and kw == 1 and stride == 1:
         return (x.reshape(-1, cin) @ w.reshape(cin, cout)).reshape(n, h, wd, cout)
-    ho, pt, pb = _same_pad(h, kh, stride)
-    wo, pl, pr = _same_pad(wd, kw, stride)
+    ho, pt, pb = _same_pad(h, kh, stride, symmetric_pad)
+    wo, pl, pr = _same_pad(wd, kw, stride, symmetric_pad)
     xp = np.pad(x, ((0, 0), (pt, pb), (pl, pr), (0, 0)))
     out = np.zeros((n, ho, wo, cout), dtype=x.dtype)
     for i in range(kh):
@@ -84,12 +90,12 @@ def conv2d_same(x: np.ndarray, w: np.ndarray, stride: int) -> np.ndarray:
     return out
 
 
-def depthwise_same(x: np.ndarray, w: np.ndarray, stride: int) -> np.ndarray:
+def depthwise_same(x: np.ndarray, w: np.ndarray, stride: int, symmetric_pad: bool = False) -> np.ndarray:
     """NHWC depthwise conv, kernel [kh,kw,C,1], TF 'SAME' padding."""
     n, h, wd, c = x.shape
     kh, kw = w.shape[:2]
-    ho, pt, pb = _same_pad(h, kh, stride)
-    wo, pl, pr = _same_pad(wd, kw, stride)
+    ho, pt, pb = _same_pad(h, kh, stride, symmetric_pad)
+    wo, pl, pr = _same_pad(wd, kw, stride, symmetric_pad)
     xp = np.pad(x, ((0, 0), (pt, pb), (pl, pr), (0, 0)))
     out = np.zeros((n, ho, wo, c), dtype=x.dtype)
     for i in range(kh):
@@ -139,10 +145,11 @@ class Oracle:
     """
 
     def __init__(self, layer_names: Sequence[str], weights: Dict[str, np.ndarray],
-                 dtype=np.float64, bn_eps: float = BN_EPS):
+                 dtype=np.float64, bn_eps: float = BN_EPS, symmetric_pad: bool = False):
         self.layer_names = list(layer_names)
         self.dtype = np.dtype(dtype)
         self.bn_eps = bn_eps
+        self.symmetric_pad = bool(symmetric_pad)
         self.w = {k: np.asarray(v, dtype=self.dtype) for k, v in weights.items()}
 
     # -- single layers -------------------------------------------------------
@@ -177,7 +184,7 @@ class Oracle:
                     # inside the SE branch: 1x1 conv with bias on the (N,1,1,C) pooled tensor
                     x = conv2d_same(x, k, 1) + w[name + "/bias:0"]
                 else:
-                    x = conv2d_same(x, k, 2 if num == 1 else 1)   # only the stem conv strides
+                    x = conv2d_same(x, k, 2 if num == 1 else 1, self.symmetric_pad)   # only the stem conv strides
             elif kind == "batch_normalization":
                 x = self._bn(x, name)
             elif kind == "swish":
@@ -185,7 +192,7 @@ class Oracle:
                 if taps is not None and num == 1:
                     taps["stem"] = x.copy()
             elif kind == "depthwise_conv2d":
-                x = depthwise_same(x, w[name + "/depthwise_kernel:0"], 2 if num in DW_STRIDE2 else 1)
+                x = depthwise_same(x, w[name + "/depthwise_kernel:0"], 2 if num in DW_STRIDE2 else 1, self.symmetric_pad)
             elif kind == "lambda":
                 blk += 1
                 if taps is not None:

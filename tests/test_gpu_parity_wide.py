@@ -1,0 +1,148 @@
+"""Parity at the sizes and on the input distribution bench.py measures (BASELINE configs[1] and [2]), the decode unit
+hook, the timeout plumbing, and oracle taps for the persistent K1 variant.
+
+Tolerances:
+  fp32 parity mode, 512 / 32 uniform-random uint8 crops vs the torch-CPU float32 port of the oracle: 0.01 deg
+      (north_star's tolerance; two float32 evaluations with different summation orders)
+  bf16 (the benched mode) on the same crops: 0.6 deg;  fp16: 0.08 deg
+"""
+import numpy as np
+import pytest
+
+import whenet_oracle as wo
+from conftest import SNAP
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def port():
+    from whenet_b200 import weights
+    names, w = weights.load_snapshot(SNAP)
+    return wo.TorchCpuPort(names, w)
+
+
+@pytest.fixture(scope="module")
+def bench_crops():
+    # bench.py's synthetic input distribution: independent uniform bytes
+    return np.random.default_rng(0).integers(0, 256, (512, 224, 224, 3), dtype=np.uint8)
+
+
+@pytest.fixture(scope="module")
+def bench_ref(port, bench_crops):
+    return np.stack(port.get_angle(bench_crops), axis=1)
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 0.01), ("bf16", 0.6), ("fp16", 0.08)])
+def test_batch512_random_uint8_vs_cpu_port(prec, tol, bench_crops, bench_ref):
+    """configs[2]: one 512-crop call in the default configuration (two half-batch streams, fused tcgen05 kernels)."""
+    import whenet_b200
+    m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=512)
+    got = np.stack(m.get_angle(bench_crops), axis=1)
+    err = np.abs(got - bench_ref)
+    print("%s N=512 random uint8: max |angle - cpu port| = %.5f deg (mean %.5f)" % (prec, err.max(), err.mean()))
+    assert err.max() <= tol
+    # the same crops through the persistent K1 variant and as one stream
+    if prec != "fp32":
+        m.set_option("streams", 1)
+        one = np.stack(m.get_angle(bench_crops), axis=1)
+        assert np.array_equal(one, got)
+    m.close()
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 0.01), ("bf16", 0.6)])
+def test_batch32_random_uint8_vs_cpu_port(prec, tol, bench_crops, bench_ref):
+    """configs[1]: batch 32."""
+    import whenet_b200
+    m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=32)
+    got = np.stack(m.get_angle(bench_crops[100:132]), axis=1)
+    err = np.abs(got - bench_ref[100:132]).max()
+    print("%s N=32: max |angle - cpu port| = %.5f deg" % (prec, err))
+    assert err <= tol
+    m.close()
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16", 0.5), ("fp16", 0.05)])
+def test_sample_angles_16bit_tight(prec, tol, sample_crops, jitter_crops, golden):
+    """Sample/ + jitter crops: measured 0.25-0.33 deg (bf16) / 0.018-0.026 deg (fp16) in round 1; a 2x regression fails."""
+    import whenet_b200
+    m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=16)
+    crops = np.concatenate([sample_crops, jitter_crops])
+    got = np.stack(m.get_angle(crops), axis=1)
+    ref = np.array([[s["yaw"], s["pitch"], s["roll"]] for s in golden["samples"]] +
+                   list(zip(golden["jitter"]["yaw"], golden["jitter"]["pitch"], golden["jitter"]["roll"])))
+    err = np.abs(got - ref).max()
+    print("%s max |angle - oracle64| = %.4f deg" % (prec, err))
+    assert err <= tol
+    m.close()
+
+
+def test_decode_hook_extreme_logits():
+    """The device softmax/expectation (the head kernel's own device function) against reference utils.py:7-11 +
+    whenet.py:31-33 on logits a float32 exp() overflows on without the max subtraction."""
+    import whenet_b200
+    m = whenet_b200.WHENet(None, device=0, precision="fp32", max_batch=8)
+    rng = np.random.default_rng(5)
+    rows = []
+    rows.append(np.full(252, 1e4, np.float32))                    # all huge and equal -> uniform
+    rows.append(np.full(252, -1e4, np.float32))
+    r = np.full(252, -1e4, np.float32); r[[7, 120 + 65, 186 + 0]] = 1e4; rows.append(r)      # one-hot at the extremes
+    r = rng.uniform(-1e4, 1e4, 252).astype(np.float32); rows.append(r)
+    r = rng.normal(0, 3, 252).astype(np.float32); rows.append(r)
+    r = (rng.normal(0, 3, 252) + 9e3).astype(np.float32); rows.append(r)                     # large common offset
+    r = np.zeros(252, np.float32); r[50] = 88.0; r[51] = 88.5; rows.append(r)                # exp(88.x) ~ FLT_MAX
+    logits = np.stack(rows)
+    got = m.debug_decode(logits)
+    ref = np.stack(wo.decode(logits[:, :120].copy(), logits[:, 120:186].copy(), logits[:, 186:].copy()), axis=1)
+    assert np.isfinite(got).all()
+    assert np.abs(got - ref).max() < 2e-3, (got, ref)
+    assert abs(got[0, 0] - (59.5 * 3 - 180)) < 1e-3 and abs(got[2, 0] - (7 * 3 - 180)) < 1e-3
+    assert abs(got[2, 1] - (65 * 3 - 99)) < 1e-3 and abs(got[2, 2] - (-99)) < 1e-3
+    m.close()
+
+
+@pytest.mark.parametrize("n", [8, 96])
+def test_timeout_flag_reaches_every_sync_path(n, sample_crops, jitter_crops):
+    """A raised mbarrier-timeout flag must fail the call that synchronises - on the single-stream path (n < 64) and on the
+    two-stream path (n >= 64, the default for the benched batch), and through whenet_synchronize for device outputs."""
+    import torch
+    import whenet_b200
+    m = whenet_b200.WHENet(SNAP, device=0, precision="bf16", max_batch=128)
+    crops = np.concatenate([sample_crops, jitter_crops] * 12)[:n]
+    ok = np.stack(m.get_angle(crops), axis=1)
+    m.debug_raise_timeout()
+    with pytest.raises(whenet_b200.WhenetError, match="timed out"):
+        m.get_angle(crops)
+    again = np.stack(m.get_angle(crops), axis=1)                   # the flag was consumed: the context stays usable
+    assert np.array_equal(ok, again)
+    x = torch.from_numpy(crops).cuda()
+    y = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    m.debug_raise_timeout()
+    m.forward_device(x, y)
+    with pytest.raises(whenet_b200.WhenetError, match="timed out"):
+        m.synchronize()
+    m.synchronize()
+    m.close()
+
+
+def test_k1p_oracle_taps(oracle32, sample_crops, jitter_crops):
+    """The persistent warp-specialised K1 variant (blocks with several tiles per crop) against the ORACLE's taps, not just
+    against K1: depthwise outputs, SE gates and block outputs of blocks 2-6, and the final angles."""
+    import whenet_b200
+    crops = np.concatenate([sample_crops, jitter_crops])
+    m = whenet_b200.WHENet(SNAP, device=0, precision="bf16", max_batch=8)
+    m.set_option("k1_variant", 3)
+    m.set_option("k1p_min_crops", 1)
+    taps = {}
+    ref_ang = np.stack(oracle32.get_angle(crops, taps), axis=1)
+    m.enable_taps(True)
+    got = np.stack(m.get_angle(crops), axis=1)
+    for i in range(2, 7):
+        for kind in ("dw", "gate", "block"):
+            nm = "%s%d" % (kind, i)
+            ref = taps[nm].astype(np.float64).reshape(-1)
+            g = m.tap(nm).astype(np.float64)
+            e = float(np.sqrt(((g - ref) ** 2).mean()) / (np.sqrt((ref ** 2).mean()) + 1e-30))
+            assert e < 0.12, (nm, e)
+    assert np.abs(got - ref_ang).max() < 0.5
+    m.close()

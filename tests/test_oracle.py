@@ -52,6 +52,13 @@ def test_wrong_bn_eps_moves_angles(sample_crops, oracle64):
     assert d > 0.3
 
 
+def test_wrong_padding_moves_angles(sample_crops, oracle64):
+    """PyTorch-style symmetric padding instead of TF 'SAME' (SURVEY.md 8c measured 16.6 deg): must be far outside any tolerance."""
+    bad = wo.load_oracle(SNAP, np.float64, symmetric_pad=True)
+    d = max(np.abs(x - y).max() for x, y in zip(bad.get_angle(sample_crops), oracle64.get_angle(sample_crops)))
+    assert d > 1.0
+
+
 def test_batch_composition_irrelevant(oracle64, sample_crops):
     both = oracle64.get_angle(sample_crops)
     one = oracle64.get_angle(sample_crops[1:2])
