@@ -13,7 +13,7 @@ N=128 REPS=2 OPTS=k1_variant=3,streams=1 timeout 600 ncu --set full --clock-cont
 python tools/ncu_summary.py gpurun_out/c1_k1p.ncu-rep gpurun_out/c1_k1p_summary.txt >> gpurun_out/c1_ncu_k1p.log 2>&1
 python tools/ncu_source.py gpurun_out/c1_k1p.ncu-rep gpurun_out/c1_k1p_source.txt 60 >> gpurun_out/c1_ncu_k1p.log 2>&1
 # ncu: the K1 launches of blocks 7-16 (second forward)
-N=128 REPS=2 OPTS=streams=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k1_expand_dw -s 16 -c 15 -o gpurun_out/c1_k1 python tools/prof_run.py > gpurun_out/c1_ncu_k1.log 2>&1
+N=128 REPS=2 OPTS=streams=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k1_expand_dw -s 16 -c 16 -o gpurun_out/c1_k1 python tools/prof_run.py > gpurun_out/c1_ncu_k1.log 2>&1
 python tools/ncu_summary.py gpurun_out/c1_k1.ncu-rep gpurun_out/c1_k1_summary.txt >> gpurun_out/c1_ncu_k1.log 2>&1
 python tools/ncu_source.py gpurun_out/c1_k1.ncu-rep gpurun_out/c1_k1_source.txt 50 >> gpurun_out/c1_ncu_k1.log 2>&1
 ls -la gpurun_out/ | tail -30
