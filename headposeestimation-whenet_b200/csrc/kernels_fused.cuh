@@ -128,6 +128,22 @@ __device__ __forceinline__ uint32_t sw128(int r, int c) {
 // (x + 0.5) / d is at least 0.5 / d away from every integer, far more than the float rounding error
 __device__ __forceinline__ int div_small(int x, float inv) { return __float2int_rz(((float)x + 0.5f) * inv); }
 
+// tcgen05.ld without the wait, and a wait that carries the destination registers as in/out operands so that no consumer
+// can be scheduled above it: lets the load of the next 16 columns fly while the current ones are being processed
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
+
 // NOEXP: the block has no expand conv (block 1): the halo tile of the block INPUT is copied straight into E and only the
 // depthwise half of the kernel runs (single chunk, no tensor-core work).
 // CCT != 0 bakes the chunk width (and with it the E row pitch and every constant-table offset) into the code: the

@@ -1,0 +1,567 @@
+// kernels_k1w.cuh - K1W: weight-stationary, persistent, warp-specialised front half of an MBConv block.
+//
+//   expand 1x1 (tcgen05, fp32 accumulators in TMEM) -> + BN shift -> swish -> 16-bit E tile in shared memory (never HBM)
+//   -> depthwise KSxKS stride S, TF-SAME (fp32 FFMA2 on the E tile) -> + BN shift -> swish
+//   -> D (global, 16-bit) + deterministic SE squeeze partial sums
+//
+// Same arithmetic as K1 (kernels_fused.cuh), different machine mapping.  K1 gives one CTA one tile and walks its phases
+// behind CTA-wide barriers; on B200 that leaves the SM at ~50 % issue utilisation in the early blocks and latency-bound
+// (one 512-thread CTA per SM, 6-18 serial chunks per crop) in the late ones.  K1W instead:
+//
+//   * a CTA owns ONE chunk of CC expanded channels for the whole launch: its slice of the expand weights (TMA, once), its
+//     BN shifts and its depthwise constants stay in shared memory ("weight stationary"), and it loops over ITEMS
+//     = (crop [pair], output tile); grid = n_chunks x groups <= #SMs, items are dealt round-robin to the groups;
+//   * the halo tile of the block INPUT of an item arrives by ONE TMA box per 64-channel K block
+//     (cp.async.bulk.tensor.4d over the NHWC tensor, SWIZZLE_128B = the UMMA K-major operand layout, rows = halo
+//     pixels in raster order).  Out-of-image halo pixels and channels past Cin are zero-filled by the TMA unit, so
+//     TF-SAME padding and K padding cost no instructions;
+//   * warp roles, connected by mbarriers (no CTA-wide barrier in the item loop):
+//       warp 0            TMA producer   A ring (NA stages)
+//       warp 1            MMA issuer     tcgen05.mma into a 2-deep TMEM accumulator ring, tcgen05.commit -> mbarrier
+//       warps 4..4+E-1    epilogue       TMEM -> +shift -> swish -> 16-bit -> E ring (2 deep); rows outside the image -> 0
+//       remaining warps   depthwise      E -> k x k FFMA2 -> +shift, swish -> D, squeeze sums (named barrier in the group)
+//     so the SFU-bound epilogue of item i+1, the FMA-bound depthwise of item i, the tensor core and the TMA unit all run
+//     at the same time.
+//
+// E row index == GEMM row index == raster index of the halo pixel, so neither the epilogue nor the depthwise needs
+// a division to find its data.  Every mbarrier wait is bounded (flag in mapped host memory + fast exit).
+#pragma once
+#include <cuda.h>
+
+#include "kernels_fused.cuh"
+
+namespace whenet {
+namespace fused {
+
+struct alignas(64) K1WParams {
+    CUtensorMap tmA;       // block input  [N][Hin][Hin][Cin]  (dims innermost first: C, W, H, N), box {64, IW, IH, NB}, SWIZZLE_128B
+    CUtensorMap tmW;       // 0.5 * BN-folded expand weights [Cexp][Cin] K-major, box {64, CC}, SWIZZLE_128B
+    const float* shift;    // [Cexp]        0.5 * BN shift of the expand conv
+    const float* w_dw;     // [KS*KS][Cexp] 0.5 * BN-folded depthwise weights
+    const float* b_dw;     // [Cexp]        0.5 * BN shift of the depthwise conv
+    void* out;             // T [N][Ho][Ho][Cexp]
+    float* partial;        // [N][tiles][Cexp]
+    int* tflag;            // mbarrier-timeout flag (mapped pinned host memory)
+    int Hin, Ho, Cin, Cexp, pad;
+    int TH, TW, IH, IW, tiles_x, tiles;
+    int NB;                // crops per item (> 1 only when one tile is the whole image)
+    int N, items;          // crops in this launch, items = ceil(N / NB) * tiles
+    int CC, n_chunks, groups;
+    int nkb;               // 64-channel K blocks of the input
+    int ksteps;            // K = 16 MMA steps = ceil(Cin / 16)
+    int mtiles;            // 128-row GEMM tiles of one item
+    int rows;              // GEMM rows of one item = NB * IH * IW
+    int rows_alloc;        // A rows per K block in shared memory (rows rounded up to 8)
+    int tbuf_cols, tmem_cols;
+    uint32_t idesc;
+    int pitchE;            // bytes per E row = CC * 2 + 16
+    int e_rows;            // E rows per crop (IH * IW + slack for ragged strips)
+    int NA;                // A ring depth (1 or 2)
+    int n_epi;             // epilogue warps: 4 (one per TMEM lane quadrant) or 8
+    int n_dw;              // depthwise threads
+    int PY, PYc;           // strip lanes (all crops of the item / per crop)
+    int spr_log2;          // log2(strips per output row)
+    uint32_t a_stage, a_tx, w_tx;               // bytes of one A stage, of its TMA transactions, of the W chunk
+    uint32_t off_w, off_c, off_e, e_buf, off_r;  // shared-memory offsets from the 1024-aligned base (A is at 0)
+};
+
+namespace k1w {
+
+// Bounded wait.  try_wait gets a suspend-time hint (ns): the warp sleeps in hardware until the phase completes instead of
+// re-polling every ~150 cycles - ncu showed the re-poll loop of K1P at 22 % of all issued instructions, stolen from the
+// warps that had work.  256 x 4 ms bounds a protocol bug to about a second; then the flag is raised and every role of the
+// CTA falls through its remaining waits.
+__device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int* tflag) {
+    if (*abort_flag) return;
+    const uint32_t addr = tc::smem_u32(bar);
+    for (uint32_t it = 0; it < 256u; ++it) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity), "r"(4000000u) : "memory");
+        if (done) return;
+        if (*abort_flag) return;
+    }
+    *abort_flag = 1;
+    *reinterpret_cast<volatile int*>(tflag) = 1;
+}
+__device__ __forceinline__ void arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(tc::smem_u32(bar)) : "memory");
+}
+// two fp32 adds in one instruction
+__device__ __forceinline__ float2 fadd2(const float2& a, const float2& b) {
+    float2 d;
+    asm("add.rn.f32x2 %0, %1, %2;"
+        : "=l"(reinterpret_cast<unsigned long long&>(d))
+        : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+    return d;
+}
+// swish of two values that are already x/2: h + h * tanh(h)
+__device__ __forceinline__ float2 swish2_from_half(const float2& h) {
+    float2 t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+    float2 d = h;
+    ffma2(d, h, t);
+    return d;
+}
+
+constexpr int kCtrlThreads = 128;      // warps 0-3: TMA producer, MMA issuer, two idle warps (the epilogue must start on a
+                                       // warp whose index is a multiple of 4: TMEM lane quadrant = warp & 3)
+}  // namespace k1w
+
+template <typename T, int KS, int S, int R, int NT>
+__global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_a_full[2], bar_a_empty[2], bar_t_full[2], bar_t_empty[2], bar_e_full[2], bar_e_empty[2], bar_w;
+    __shared__ uint32_t s_tmem_base;
+    __shared__ int s_abort_mem;
+    volatile int* s_abort = &s_abort_mem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = smem0, sW = smem0 + p.off_w, sC = smem0 + p.off_c, sE = smem0 + p.off_e, sR = smem0 + p.off_r;
+    const int CC = p.CC, pitchE = p.pitchE;
+    const int chunk = blockIdx.x % p.n_chunks, group = blockIdx.x / p.n_chunks;
+    const int cbase = chunk * CC;
+    const int n_epi_threads = 32 * p.n_epi;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&bar_a_full[i], 1);
+            tc::mbar_init(&bar_a_empty[i], 1);
+            tc::mbar_init(&bar_t_full[i], 1);
+            tc::mbar_init(&bar_t_empty[i], n_epi_threads);
+            tc::mbar_init(&bar_e_full[i], n_epi_threads);
+            tc::mbar_init(&bar_e_empty[i], p.n_dw);
+        }
+        tc::mbar_init(&bar_w, 1);
+        s_abort_mem = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&s_tmem_base)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = s_tmem_base;
+
+    // item -> geometry.  An item is (crop n0 .. n0+NB-1, output tile): origin of the output tile and of its input halo tile.
+    const float inv_tiles = 1.0f / (float)p.tiles, inv_tx = 1.0f / (float)p.tiles_x;
+    struct Geo { int n0, tile, ty0, tx0, iy0, ix0; };
+    auto geom = [&](int item) {
+        Geo g;
+        const int q = div_small(item, inv_tiles);
+        g.n0 = q * p.NB;
+        g.tile = item - q * p.tiles;
+        const int tyi = div_small(g.tile, inv_tx);
+        g.ty0 = tyi * p.TH;
+        g.tx0 = (g.tile - tyi * p.tiles_x) * p.TW;
+        g.iy0 = g.ty0 * S - p.pad;
+        g.ix0 = g.tx0 * S - p.pad;
+        return g;
+    };
+
+    if (warp == 0) {
+        // =========================================================================== TMA producer
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW) : "memory");
+            // this CTA's slice of the expand weights: resident for the whole launch
+            k1w::arrive_expect_tx(&bar_w, p.w_tx);
+            for (int kb = 0; kb < p.nkb; ++kb) k1w::tma_2d(sW + (uint32_t)kb * CC * 128, &p.tmW, kb * 64, cbase, &bar_w);
+            int k = 0;
+            for (int item = group; item < p.items; item += p.groups, ++k) {
+                const Geo g = geom(item);
+                const int st = p.NA == 2 ? (k & 1) : 0;
+                const uint32_t par = p.NA == 2 ? ((k >> 1) & 1) : (k & 1);
+                k1w::wait(&bar_a_empty[st], par ^ 1, s_abort, p.tflag);         // the MMAs that read this stage have completed
+                k1w::arrive_expect_tx(&bar_a_full[st], p.a_tx);
+                for (int kb = 0; kb < p.nkb; ++kb)
+                    k1w::tma_4d(sA + (uint32_t)st * p.a_stage + (uint32_t)kb * p.rows_alloc * 128, &p.tmA, kb * 64, g.ix0, g.iy0, g.n0, &bar_a_full[st]);
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================================== MMA issuer
+        k1w::wait(&bar_w, 0, s_abort, p.tflag);
+        int k = 0;
+        for (int item = group; item < p.items; item += p.groups, ++k) {
+            const int st = p.NA == 2 ? (k & 1) : 0;
+            const uint32_t par = p.NA == 2 ? ((k >> 1) & 1) : (k & 1);
+            const int tb = k & 1;
+            k1w::wait(&bar_a_full[st], par, s_abort, p.tflag);
+            k1w::wait(&bar_t_empty[tb], ((k >> 1) & 1) ^ 1, s_abort, p.tflag);  // the epilogue has drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0 && !*s_abort) {
+                const uint32_t a0 = sA + (uint32_t)st * p.a_stage;
+                for (int mt = 0; mt < p.mtiles; ++mt)
+                    for (int ks = 0; ks < p.ksteps; ++ks) {
+                        const int kb = ks >> 2, kk = ks & 3;
+                        const uint64_t ad = tc::make_desc(a0 + (uint32_t)kb * p.rows_alloc * 128 + (uint32_t)mt * BM * 128);
+                        const uint64_t bd = tc::make_desc(sW + (uint32_t)kb * CC * 128);
+                        tc::umma_f16(tmem_base + (uint32_t)(tb * p.tbuf_cols + mt * CC), ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2),
+                                     p.idesc, ks ? 1u : 0u);
+                    }
+                tc::umma_commit(&bar_t_full[tb]);
+                tc::umma_commit(&bar_a_empty[st]);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4 && warp < 4 + p.n_epi) {
+        // =========================================================================== epilogue: TMEM -> +shift -> swish -> E
+        const int q4 = warp & 3;                       // TMEM lane quadrant of this warp
+        const int grp = (warp - 4) >> 2, NG = p.n_epi >> 2;
+        const int units = CC >> 4;
+        const int npix = p.IH * p.IW;
+        const float inv_IW = 1.0f / (float)p.IW, inv_npix = 1.0f / (float)npix;
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        // BN shifts of this CTA's channels -> shared memory (read by this group only; published by a group barrier)
+        {
+            float* sh = reinterpret_cast<float*>(smem_raw + (sC - tc::smem_u32(smem_raw)));
+            for (int c = tid - k1w::kCtrlThreads; c < CC; c += n_epi_threads) sh[c] = p.shift[cbase + c];
+            asm volatile("bar.sync 2, %0;" ::"r"(n_epi_threads) : "memory");
+        }
+        int k = 0;
+        for (int item = group; item < p.items; item += p.groups, ++k) {
+            const Geo g = geom(item);
+            const int buf = k & 1;
+            // rows of this thread: r = mt * 128 + q4 * 32 + lane.  In range (part of the box) / inside the image?
+            bool in_box[3], in_img[3];
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt) {
+                const int r = mt * BM + q4 * 32 + lane;
+                in_box[mt] = r < p.rows;
+                const int rc = in_box[mt] ? r : 0;
+                const int j = p.NB == 1 ? 0 : div_small(rc, inv_npix);
+                const int q = rc - j * npix;
+                const int ty = div_small(q, inv_IW), tx = q - ty * p.IW;
+                const int iy = g.iy0 + ty, ix = g.ix0 + tx;
+                in_img[mt] = in_box[mt] && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Hin && g.n0 + j < p.N;
+            }
+            int mt_count = 0;
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt) mt_count += (mt < p.mtiles && mt * BM + q4 * 32 < p.rows) ? 1 : 0;   // a prefix of the tiles
+            const int n_pairs = mt_count * units;
+            k1w::wait(&bar_t_full[buf], (k >> 1) & 1, s_abort, p.tflag);
+            k1w::wait(&bar_e_empty[buf], ((k >> 1) & 1) ^ 1, s_abort, p.tflag);     // the depthwise of item k-2 is done with this E
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (!*s_abort) {
+                // E rows of the NB crops are e_rows apart; row r of the box belongs to crop r / npix
+                const uint32_t e0 = sE + (uint32_t)buf * p.e_buf;
+                const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * p.tbuf_cols);
+                auto e_addr = [&](int mt) {
+                    const int r = mt * BM + q4 * 32 + lane;
+                    if (p.NB == 1) return e0 + (uint32_t)r * pitchE;
+                    const int j = div_small(r < p.rows ? r : 0, inv_npix);
+                    return e0 + (uint32_t)(j * p.e_rows + (r - j * npix)) * pitchE;
+                };
+                const uint32_t ea[3] = {e_addr(0), e_addr(1), e_addr(2)};
+                auto col_of = [&](int f) { const int mt = f >= 2 * units ? 2 : (f >= units ? 1 : 0); return (uint32_t)(mt * CC + (f - mt * units) * 16); };
+                auto process = [&](uint32_t (&r)[16], int f) {
+                    const int mt = f >= 2 * units ? 2 : (f >= units ? 1 : 0), u = f - mt * units;
+                    const bool box = mt == 0 ? in_box[0] : (mt == 1 ? in_box[1] : in_box[2]);
+                    const bool img = mt == 0 ? in_img[0] : (mt == 1 ? in_img[1] : in_img[2]);
+                    const uint32_t dst = (mt == 0 ? ea[0] : (mt == 1 ? ea[1] : ea[2])) + u * 32;
+                    if (img) {
+                        uint32_t o[8];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 sh = lds_f4(sC + (uint32_t)(u * 16 + j * 4) * 4);
+                            const float2 a = k1w::swish2_from_half(k1w::fadd2(make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), make_float2(sh.x, sh.y)));
+                            const float2 b = k1w::swish2_from_half(k1w::fadd2(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), make_float2(sh.z, sh.w)));
+                            o[2 * j] = pack2<T>(a.x, a.y);
+                            o[2 * j + 1] = pack2<T>(b.x, b.y);
+                        }
+                        sts128(dst, make_uint4(o[0], o[1], o[2], o[3]));
+                        sts128(dst + 16, make_uint4(o[4], o[5], o[6], o[7]));
+                    } else if (box) {
+                        // halo pixel outside the image (or crop past the batch): the depthwise pads the EXPANDED tensor with zeros
+                        sts128(dst, zero);
+                        sts128(dst + 16, zero);
+                    }
+                };
+                uint32_t ra[16], rb[16];
+                int f = grp;
+                if (f < n_pairs) tmem_ld16_issue(t0 + col_of(f), ra);
+                while (f < n_pairs) {
+                    tmem_ld16_wait(ra);
+                    const int f2 = f + NG;
+                    if (f2 < n_pairs) tmem_ld16_issue(t0 + col_of(f2), rb);     // flies while ra is processed
+                    process(ra, f);
+                    if (f2 >= n_pairs) break;
+                    tmem_ld16_wait(rb);
+                    const int f3 = f2 + NG;
+                    if (f3 < n_pairs) tmem_ld16_issue(t0 + col_of(f3), ra);
+                    process(rb, f2);
+                    f = f3;
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            k1w::arrive(&bar_t_empty[buf]);
+            k1w::arrive(&bar_e_full[buf]);
+        }
+    } else if (warp >= 4 + p.n_epi) {
+        // =========================================================================== depthwise on E
+        const int dtid = tid - (k1w::kCtrlThreads + n_epi_threads);
+        const int CVc = CC >> 2;
+        const int py = div_small(dtid, 1.0f / (float)CVc), cv = dtid - py * CVc;
+        const int jc = p.NB == 1 ? 0 : div_small(py, 1.0f / (float)p.PYc), pl = py - jc * p.PYc;   // crop of this lane, lane within the crop
+        const bool lane_ok = py < p.PY;
+        const int nstrips = p.TH << p.spr_log2;
+        const uint32_t e_rowstride = (uint32_t)p.IW * pitchE;
+        constexpr int NCOL = (R - 1) * S + KS;
+        // depthwise constants of this CTA's channels: { b_dw[CC], w_dw[KS*KS][CC] } fp32, staged once by this group
+        {
+            float* cst = reinterpret_cast<float*>(smem_raw + (sC - tc::smem_u32(smem_raw))) + CC;
+            for (int i = dtid; i < (KS * KS + 1) * CC; i += p.n_dw) {
+                const int row = div_small(i, 1.0f / (float)CC), c = i - row * CC;
+                cst[i] = row == 0 ? p.b_dw[cbase + c] : p.w_dw[(long long)(row - 1) * p.Cexp + cbase + c];
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(p.n_dw) : "memory");
+        }
+        const uint32_t cst = sC + (uint32_t)CC * 4 + (uint32_t)cv * 16;         // this thread's column of the constants
+        const int c0 = cbase + cv * 4;
+        T* const out = reinterpret_cast<T*>(p.out);
+        int k = 0;
+        for (int item = group; item < p.items; item += p.groups, ++k) {
+            const Geo g = geom(item);
+            const int buf = k & 1;
+            const bool dw_active = lane_ok && g.n0 + jc < p.N;
+            T* const out_n = out + (long long)(g.n0 + jc) * p.Ho * p.Ho * p.Cexp;
+            k1w::wait(&bar_e_full[buf], (k >> 1) & 1, s_abort, p.tflag);
+            float sum[4] = {0.f, 0.f, 0.f, 0.f};
+            if (dw_active) {
+                const float4 bq = lds_f4(cst);
+                const uint32_t e_cv = sE + (uint32_t)buf * p.e_buf + (uint32_t)(jc * p.e_rows) * pitchE + (uint32_t)cv * 8;
+                for (int sidx = pl; sidx < nstrips; sidx += p.PYc) {
+                    const int oyl = sidx >> p.spr_log2, oxl0 = (sidx - (oyl << p.spr_log2)) * R;
+                    float2 acc[R][2];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) { acc[r][0] = make_float2(bq.x, bq.y); acc[r][1] = make_float2(bq.z, bq.w); }
+                    uint32_t erow = e_cv + (uint32_t)(oyl * S) * e_rowstride + (uint32_t)(oxl0 * S) * pitchE;
+#pragma unroll
+                    for (int ky = 0; ky < KS; ++ky) {
+                        float2 wr[KS][2];
+#pragma unroll
+                        for (int kx = 0; kx < KS; ++kx) {
+                            const float4 wq = lds_f4(cst + (uint32_t)((1 + ky * KS + kx) * CC) * 4);
+                            wr[kx][0] = make_float2(wq.x, wq.y); wr[kx][1] = make_float2(wq.z, wq.w);
+                        }
+                        uint32_t ea = erow;
+#pragma unroll
+                        for (int col = 0; col < NCOL; ++col) {
+                            uint32_t a, b;
+                            lds64(ea, a, b);
+                            ea += pitchE;
+                            float2 x01, x23;
+                            unpack2<T>(a, x01.x, x01.y);
+                            unpack2<T>(b, x23.x, x23.y);
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+                                const int kx = col - r * S;          // compile-time after unrolling
+                                if (kx >= 0 && kx < KS) {
+                                    ffma2(acc[r][0], x01, wr[kx][0]);
+                                    ffma2(acc[r][1], x23, wr[kx][1]);
+                                }
+                            }
+                        }
+                        erow += e_rowstride;
+                    }
+                    const int oy = g.ty0 + oyl;
+                    T* dst = out_n + ((long long)oy * p.Ho + g.tx0 + oxl0) * p.Cexp + c0;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (oxl0 + r < p.TW) {
+                            const float2 s01 = k1w::swish2_from_half(acc[r][0]), s23 = k1w::swish2_from_half(acc[r][1]);
+                            sum[0] += s01.x; sum[1] += s01.y; sum[2] += s23.x; sum[3] += s23.y;
+                            uint2 o;
+                            o.x = pack2<T>(s01.x, s01.y);
+                            o.y = pack2<T>(s23.x, s23.y);
+                            *reinterpret_cast<uint2*>(dst + (long long)r * p.Cexp) = o;
+                        }
+                    }
+                }
+            }
+            k1w::arrive(&bar_e_empty[buf]);                   // every depthwise thread: its reads of this E are done
+            // squeeze partial sums of the item: lanes -> shared memory -> one fixed-order column sum per (crop, channel)
+            const uint32_t r_buf = sR + (uint32_t)(buf * p.PY * CC) * 4;
+            if (lane_ok)
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(r_buf + (uint32_t)(py * CC + cv * 4) * 4),
+                             "f"(sum[0]), "f"(sum[1]), "f"(sum[2]), "f"(sum[3]) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"r"(p.n_dw) : "memory");
+            if (dtid < p.NB * CC) {
+                const int jj = dtid >= CC ? 1 : 0, cc = dtid - jj * CC;          // NB <= 2
+                if (g.n0 + jj < p.N) {
+                    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+                    const uint32_t r0 = r_buf + (uint32_t)(jj * p.PYc * CC + cc) * 4;
+                    int y = 0;
+                    for (; y + 3 < p.PYc; y += 4) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float t;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(r0 + (uint32_t)((y + i) * CC) * 4));
+                            s4[i] += t;
+                        }
+                    }
+                    for (; y < p.PYc; ++y) {
+                        float t;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(r0 + (uint32_t)(y * CC) * 4));
+                        s4[y & 3] += t;
+                    }
+                    p.partial[((long long)(g.n0 + jj) * p.tiles + g.tile) * p.Cexp + cbase + cc] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                }
+            }
+            // the squeeze scratch of this parity is rewritten two items later, after the next named barrier
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+}
+
+// ----------------------------------------------------------------------------- planning (host)
+// TH x TW output tile, R outputs per strip, CC channels per CTA, NB crops per item, n_epi epilogue warps, NT threads.
+// Fills every field of K1WParams except the tensor maps and the pointers.  false = this plan cannot run.
+inline bool plan_k1w_candidate(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, bool is_bf16, int TH, int TW, int R, int CC, int NB,
+                               int n_epi, int NT, K1WParams* p, size_t* smem_out) {
+    if (Ho % TH || Ho % TW || Cexp % CC || (CC & 15) || CC > 256 || (n_epi != 4 && n_epi != 8) || NB < 1 || NB > 2) return false;
+    p->Hin = Hin; p->Ho = Ho; p->Cin = Cin; p->Cexp = Cexp; p->pad = pad;
+    p->TH = TH; p->TW = TW;
+    p->IH = (TH - 1) * s + k; p->IW = (TW - 1) * s + k;
+    p->tiles_x = Ho / TW; p->tiles = p->tiles_x * (Ho / TH);
+    if (NB > 1 && p->tiles != 1) return false;
+    if (p->IH > 256 || p->IW > 256) return false;
+    p->NB = NB;
+    p->CC = CC; p->n_chunks = Cexp / CC;
+    p->nkb = (Cin + 63) / 64;
+    p->ksteps = (Cin + 15) / 16;
+    p->rows = NB * p->IH * p->IW;
+    p->mtiles = (p->rows + BM - 1) / BM;
+    if (p->mtiles > 3) return false;
+    p->rows_alloc = (p->rows + 7) & ~7;
+    p->tbuf_cols = p->mtiles * CC;
+    int cols = 32;
+    while (cols < 2 * p->tbuf_cols) cols <<= 1;
+    if (cols > 512) return false;
+    p->tmem_cols = cols;
+    p->idesc = tc::make_idesc(is_bf16, CC);
+    p->pitchE = CC * 2 + 16;
+    p->e_rows = p->IH * p->IW + R * s + 16;          // a ragged strip still LOADS the columns of its discarded outputs
+    p->n_epi = n_epi;
+    p->n_dw = NT - k1w::kCtrlThreads - 32 * n_epi;
+    if (p->n_dw < 64 || (p->n_dw & 31)) return false;
+    const int CVc = CC / 4;
+    p->PYc = p->n_dw / CVc / NB;
+    p->PY = p->PYc * NB;
+    if (p->PYc < 1 || NB * CC > p->n_dw) return false;
+    const int spr = (TW + R - 1) / R;
+    p->spr_log2 = spr == 1 ? 0 : spr == 2 ? 1 : spr == 4 ? 2 : -1;
+    if (p->spr_log2 < 0) return false;
+    p->a_stage = (uint32_t)p->nkb * p->rows_alloc * 128;                      // multiple of 1024
+    p->a_tx = (uint32_t)p->nkb * p->rows * 128;                               // full boxes, zero fill included
+    p->w_tx = (uint32_t)p->nkb * CC * 128;
+    const uint32_t w_bytes = ((uint32_t)p->nkb * CC * 128 + 1023u) & ~1023u;
+    const uint32_t c_bytes = (uint32_t)((k * k + 2) * CC * 4 + 15) & ~15u;    // shift[CC] | b_dw[CC] | w_dw[k*k][CC]
+    p->e_buf = ((uint32_t)NB * p->e_rows * p->pitchE + 15u) & ~15u;
+    const uint32_t r_bytes = 2u * p->PY * CC * 4;
+    for (int na = 2; na >= 1; --na) {
+        p->NA = na;
+        p->off_w = (uint32_t)na * p->a_stage;
+        p->off_c = p->off_w + w_bytes;
+        p->off_e = p->off_c + c_bytes;
+        p->off_r = p->off_e + 2 * p->e_buf;
+        const size_t total = (size_t)p->off_r + r_bytes + 1024;
+        // the UMMA of the last M tile reads 128 rows even when fewer were staged: that read has to stay inside the window
+        const size_t over = (size_t)(na - 1) * p->a_stage + (size_t)(p->nkb - 1) * p->rows_alloc * 128 + (size_t)p->mtiles * BM * 128 + 1024;
+        if (total <= K1_MAX_SMEM && over <= total) { *smem_out = total; return true; }
+    }
+    return false;
+}
+
+struct K1WChoice { int th, tw, r, cc, nb, n_epi, nt; };
+
+// Per-block plan table (first guesses from the per-role instruction model in DESIGN.md; tools/tune_k1w.py re-measures them).
+inline bool plan_k1w(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, bool is_bf16, K1WParams* p, K1WChoice* choice, size_t* smem_out) {
+    struct Tuned { int hin, k, s, cexp; K1WChoice c; };
+    static const Tuned tuned[] = {
+        {112, 3, 2, 96, {8, 8, 4, 48, 1, 8, 768}},      // block 2: 17x17 halo = 289 rows, SFU-bound -> 8 epilogue warps
+        {56, 3, 1, 144, {14, 14, 7, 48, 1, 4, 640}},    // block 3: 16x16 = 256 rows
+        {56, 5, 2, 144, {7, 7, 4, 48, 1, 8, 768}},      // block 4: 17x17
+        {28, 5, 1, 240, {14, 14, 7, 48, 1, 4, 640}},    // block 5: 18x18 = 324 rows
+        {28, 3, 2, 240, {7, 7, 4, 48, 1, 8, 768}},      // block 6: 15x15 = 225 rows
+        {14, 3, 1, 480, {14, 14, 7, 48, 1, 4, 640}},    // blocks 7, 8: whole image, 16x16
+        {14, 5, 1, 480, {14, 14, 7, 48, 1, 4, 640}},    // block 9: 18x18
+        {14, 5, 1, 672, {14, 14, 7, 48, 1, 4, 640}},    // blocks 10, 11
+        {14, 5, 2, 672, {7, 7, 4, 48, 1, 8, 768}},      // block 12: 17x17
+        {7, 5, 1, 1152, {7, 7, 4, 48, 2, 4, 640}},      // blocks 13-15: two crops per item, 2 x 11x11 = 242 rows
+        {7, 3, 1, 1152, {7, 7, 4, 48, 2, 4, 640}},      // block 16: 2 x 9x9 = 162 rows
+    };
+    for (const Tuned& t : tuned)
+        if (t.hin == Hin && t.k == k && t.s == s && t.cexp == Cexp) {
+            K1WParams q{};
+            size_t smem = 0;
+            if (plan_k1w_candidate(Hin, Ho, Cin, Cexp, k, s, pad, is_bf16, t.c.th, t.c.tw, t.c.r, t.c.cc, t.c.nb, t.c.n_epi, t.c.nt, &q, &smem)) {
+                *p = q; *choice = t.c; *smem_out = smem;
+                return true;
+            }
+        }
+    return false;
+}
+
+inline bool k1w_has_instance(int k, int s, int R, int NT) {
+    return (k == 3 || k == 5) && (s == 1 || s == 2) && (R == 4 || R == 7) && (NT == 640 || NT == 768);
+}
+
+template <typename T>
+int launch_k1w(cudaStream_t stream, K1WParams p, int k, int s, int R, int NT, size_t smem, int n_crops, int sm_count) {
+    p.N = n_crops;
+    p.items = ((n_crops + p.NB - 1) / p.NB) * p.tiles;
+    int groups = sm_count / p.n_chunks;
+    if (groups < 1) groups = 1;
+    if (groups > p.items) groups = p.items;
+    p.groups = groups;
+    const int ctas = groups * p.n_chunks;
+    if (ctas < 1) return 0;
+#define K1W_GO(KS, S, RR, NTT)                                                                                             \
+    do {                                                                                                                   \
+        auto kfn = k1w_kernel<T, KS, S, RR, NTT>;                                                                          \
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_MAX_SMEM) != cudaSuccess) return -1;  \
+        kfn<<<ctas, NTT, smem, stream>>>(p);                                                                               \
+        return 0;                                                                                                          \
+    } while (0)
+#define K1W(KS, S, RR)                                  \
+    do {                                                \
+        if (NT == 640) K1W_GO(KS, S, RR, 640);          \
+        if (NT == 768) K1W_GO(KS, S, RR, 768);          \
+    } while (0)
+    if (k == 3 && s == 2 && R == 4) K1W(3, 2, 4);
+    if (k == 3 && s == 1 && R == 7) K1W(3, 1, 7);
+    if (k == 5 && s == 1 && R == 7) K1W(5, 1, 7);
+    if (k == 5 && s == 2 && R == 4) K1W(5, 2, 4);
+    if (k == 3 && s == 2 && R == 7) K1W(3, 2, 7);
+    if (k == 3 && s == 1 && R == 4) K1W(3, 1, 4);
+    if (k == 5 && s == 1 && R == 4) K1W(5, 1, 4);
+    if (k == 5 && s == 2 && R == 7) K1W(5, 2, 7);
+#undef K1W
+#undef K1W_GO
+    return 1;
+}
+
+}  // namespace fused
+}  // namespace whenet

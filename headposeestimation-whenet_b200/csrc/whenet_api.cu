@@ -21,6 +21,8 @@
 #include "kernels_fused.cuh"
 #include "kernels_crop.cuh"
 #include "kernels_k1p.cuh"
+#include "kernels_k1w.cuh"
+#include <cudaTypedefs.h>
 
 // The fused-kernel launchers are instantiated in their own translation units (inst_k1_bf16.cu, inst_k1_f16.cu, inst_k1x.cu)
 namespace whenet {
@@ -28,7 +30,8 @@ namespace fused {
 #define WHENET_EXTERN_FUSED(T)                                                                            \
     extern template int launch_k1<T>(cudaStream_t, K1Params, int, int, int, int, size_t, int);            \
     extern template int launch_dw_only<T>(cudaStream_t, K1Params, size_t, int);                           \
-    extern template int launch_k1p<T>(cudaStream_t, K1PParams, int, int, int, size_t, int, int);
+    extern template int launch_k1p<T>(cudaStream_t, K1PParams, int, int, int, size_t, int, int);                \
+    extern template int launch_k1w<T>(cudaStream_t, K1WParams, int, int, int, int, size_t, int, int);
 WHENET_EXTERN_FUSED(__nv_bfloat16)
 WHENET_EXTERN_FUSED(__half)
 #undef WHENET_EXTERN_FUSED
@@ -98,12 +101,19 @@ struct BlockW {   // device pointers into the fp32 arena
     float *w_se2 = nullptr, *b_se2 = nullptr;     // [cse][cexp], [cexp]
     float *w_proj = nullptr, *b_proj = nullptr;   // [cexp][cout], [cout]
     void *wt_exp = nullptr, *wt_proj = nullptr;   // 16-bit [N][K] copies for the tensor-core path
+    void* wt_exp_h = nullptr;                     // 16-bit [cexp][cin]: 0.5 * weights (K1W; its shift is b_exp_h)
+    float* b_exp_h = nullptr;                     // 0.5 * BN shift of the expand conv (K1W)
     void* wt_exp_aug = nullptr;                   // 16-bit [cexp][cin+8]: 0.5*(weights | shift_hi | shift_lo) | 0... (K1)
     float *w_dw_h = nullptr, *b_dw_h = nullptr;   // 0.5 * depthwise weights / shift (K1)
 };
 
 struct K1Plan { bool valid = false; whenet::fused::K1Params p{}; int R = 0; int NT = 256; size_t smem = 0; };
 struct K1PPlan { bool valid = false; whenet::fused::K1PParams p{}; int R = 0; size_t smem = 0; };
+struct K1WPlan { bool valid = false; whenet::fused::K1WParams p{}; int R = 0, NT = 0; size_t smem = 0; };
+struct TmapKey {
+    int block, n; const void* ptr;
+    bool operator<(const TmapKey& o) const { return block != o.block ? block < o.block : (n != o.n ? n < o.n : ptr < o.ptr); }
+};
 struct GraphKey {
     int n, in_u8, sig;
     const void* in;
@@ -138,13 +148,17 @@ struct whenet_ctx {
     int use_fused = 0;      // K1: expand + depthwise in one kernel (16-bit storage only; default on for bf16/fp16)
     int fused_max_block = 16;  // blocks 2..fused_max_block use K1
     std::vector<K1Plan> k1;
+    std::vector<K1WPlan> k1w;  // k1_variant 4: weight-stationary persistent K1 (TMA-staged input tiles)
+    std::map<TmapKey, CUtensorMap> tmaps;   // input tensor maps of K1W by (block, crops, buffer)
+    std::vector<CUtensorMap> tmap_w;        // weight tensor maps of K1W by block
     std::vector<K1PPlan> k1p;  // k1_variant 3: persistent warp-specialised K1 for the blocks with several tiles per crop
     int sm_count = 148;
     int k1p_epi_warps = 8;     // epilogue group of K1P: 4 or 8 warps (the depthwise group gets the other 10 or 6)
     int k1p_min_crops = 8;     // below this a persistent grid cannot fill the SMs: K1 with its chunk split is used instead
     K1Plan dw1;                // block 1 (no expand): depthwise-only instance of K1
     int dw1_fused = 1;
-    int k1_variant = 1;        // 1 = K1 everywhere, 3 = K1P (persistent, warp-specialised) for the blocks with several tiles per crop
+    int k1_variant = 1;        // 1 = K1 everywhere, 3 = K1P (persistent, warp-specialised) for the blocks with several tiles per crop,
+                               // 4 = K1W (weight-stationary persistent CTAs, TMA input tiles) for every block with an expand conv
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     bool weights_loaded = false;
     std::vector<BlockCfg> blocks;
@@ -301,6 +315,8 @@ int ensure_ws(whenet_ctx* c) {
     }
     for (const K1Plan& pl : c->k1)
         if (pl.valid) part = std::max(part, (size_t)pl.p.tiles_x * pl.p.tiles_y * pl.p.Cexp);
+    for (const K1WPlan& pl : c->k1w)
+        if (pl.valid) part = std::max(part, (size_t)pl.p.tiles * pl.p.Cexp);
     for (const K1PPlan& pl : c->k1p)          // persistent variant: its own tile shapes (tuning hook) size the partials too
         if (pl.valid) part = std::max(part, (size_t)pl.p.tiles * pl.p.k.Cexp);
     if (c->dw1.valid) part = std::max(part, (size_t)c->dw1.p.tiles_x * c->dw1.p.tiles_y * c->dw1.p.Cexp);
@@ -316,6 +332,46 @@ int ensure_ws(whenet_ctx* c) {
     CK(cudaMemset(c->d_se_counter, 0, ch * sizeof(int)));
     for (int i = 0; i < 2; ++i) CK(cudaMalloc(&c->d_in[i], ch * kImgElems * sizeof(float)));
     c->ws_chunk = c->chunk;
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- TMA tensor maps (K1W)
+PFN_cuTensorMapEncodeTiled_v12000 tmap_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
+    }
+    return fn;
+}
+// NHWC activation tensor [n][H][H][C] (16-bit): box = {64 channels, box_w, box_h, box_n}, SWIZZLE_128B, zero fill outside
+int make_tmap_act(CUtensorMap* tm, const void* base, int n, int H, int C, int box_w, int box_h, int box_n, bool is_bf16) {
+    auto fn = tmap_encode_fn();
+    if (!fn) return fail(WHENET_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)H, (cuuint64_t)n};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)H * C * 2, (cuuint64_t)H * H * C * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = fn(tm, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(WHENET_ECUDA, "cuTensorMapEncodeTiled(activation %dx%dx%dx%d, box %dx%dx%d) failed: %d", n, H, H, C, box_n, box_h, box_w, (int)r);
+    return 0;
+}
+// K-major weight matrix [rows][K] (16-bit): box = {64, box_rows}
+int make_tmap_w(CUtensorMap* tm, const void* base, int rows, int K, int box_rows, bool is_bf16) {
+    auto fn = tmap_encode_fn();
+    if (!fn) return fail(WHENET_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(tm, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(WHENET_ECUDA, "cuTensorMapEncodeTiled(weights %dx%d, box %d) failed: %d", rows, K, box_rows, (int)r);
     return 0;
 }
 
@@ -421,6 +477,28 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
                 if (rc != 0) return fail(WHENET_ECUDA, "depthwise-only K1 launch failed (rc=%d)", rc);
                 CK(cudaGetLastError());
                 tiles = p.tiles_x * p.tiles_y;
+                did_k1 = true;
+            } else if (c->use_fused && c->k1_variant == 4 && c->k1w[i].valid && b.idx <= c->fused_max_block) {
+                const K1WPlan& pl = c->k1w[i];
+                whenet::fused::K1WParams p = pl.p;
+                const TmapKey key{b.idx, nb, (const void*)cur};
+                auto it = c->tmaps.find(key);
+                if (it == c->tmaps.end()) {
+                    if (c->tmaps.size() > 512) c->tmaps.clear();
+                    CUtensorMap tm;
+                    int rc = make_tmap_act(&tm, cur, nb, b.hin, b.cin, p.IW, p.IH, p.NB, c->precision == WHENET_PRECISION_BF16);
+                    if (rc) return rc;
+                    it = c->tmaps.emplace(key, tm).first;
+                }
+                p.tmA = it->second; p.tmW = c->tmap_w[i];
+                p.shift = w.b_exp_h; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial; p.tflag = c->d_tflag;
+                snprintf(nm, sizeof nm, "b%02d.k1", b.idx);
+                Scope sc(c, nm, (double)nb * ((double)b.hin * b.hin * b.cin + (double)b.hout * b.hout * b.cexp) * sizeof(T),
+                         2.0 * nb * ((double)b.hin * b.hin * b.cin * b.cexp + (double)b.hout * b.hout * b.k * b.k * b.cexp));
+                int rc = whenet::fused::launch_k1w<T>(c->stream, p, b.k, b.s, pl.R, pl.NT, pl.smem, nb, c->sm_count);
+                if (rc != 0) return fail(WHENET_ECUDA, "K1W launch failed for block %d (rc=%d)", b.idx, rc);
+                CK(cudaGetLastError());
+                tiles = p.tiles;
                 did_k1 = true;
             } else if (c->use_fused && c->k1_variant == 3 && c->k1p[i].valid && nb >= c->k1p_min_crops && b.idx <= c->fused_max_block) {
                 whenet::fused::K1PParams pp = c->k1p[i].p;
@@ -741,6 +819,8 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
     c->bw.resize(c->blocks.size());
     c->k1.resize(c->blocks.size());
     c->k1p.resize(c->blocks.size());
+    c->k1w.resize(c->blocks.size());
+    c->tmap_w.resize(c->blocks.size());
     if (precision != WHENET_PRECISION_FP32) {
         const BlockCfg& b1 = c->blocks[0];
         c->dw1.valid = !b1.has_expand && whenet::fused::plan_dw_only(b1.hin, b1.cexp, b1.k, b1.s, b1.pad, &c->dw1.p, &c->dw1.smem);
@@ -756,6 +836,12 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
                                               &pl.p, &ch, &pl.smem);
             pl.R = ch.r;
             pl.NT = ch.nt;
+            {
+                K1WPlan& pw = c->k1w[i];
+                whenet::fused::K1WChoice wc{};
+                pw.valid = whenet::fused::plan_k1w(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, precision == WHENET_PRECISION_BF16, &pw.p, &wc, &pw.smem);
+                pw.R = wc.r; pw.NT = wc.nt;
+            }
             if (pl.valid && pl.p.tiles_x * pl.p.tiles_y > 1) {       // K1P: same tile, strip and chunk shape as the K1 plan
                 K1PPlan& pq = c->k1p[i];
                 pq.valid = whenet::fused::plan_k1p(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, precision == WHENET_PRECISION_BF16,
@@ -804,7 +890,7 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
                                                   while (arena.size() % 4) arena.push_back(0.f); return off; };
     auto put16 = [&](const std::vector<float>& v) { size_t off = arena16src.size(); arena16src.insert(arena16src.end(), v.begin(), v.end());
                                                     while (arena16src.size() % 8) arena16src.push_back(0.f); return off; };
-    struct Off { size_t w_exp, b_exp, w_dw, b_dw, w_se1t, b_se1, w_se2, b_se2, w_proj, b_proj, t_exp, t_proj, t_aug, w_dw_h, b_dw_h; };
+    struct Off { size_t w_exp, b_exp, w_dw, b_dw, w_se1t, b_se1, w_se2, b_se2, w_proj, b_proj, t_exp, t_proj, t_aug, w_dw_h, b_dw_h, t_exp_h, b_exp_h; };
     // values of the augmented expand weights; shift columns are filled after 16-bit rounding of the high part
     std::vector<std::pair<size_t, float>> shift_lo_fix;   // (index in arena16src of the hi column, full-precision shift)
     std::vector<Off> offs(c->blocks.size());
@@ -865,6 +951,14 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
                 aug[(size_t)n * ka + b.cin] = 0.5f * arena[o.b_exp + n];
             }
             o.t_aug = put16(aug);
+            // K1W: 0.5 * weights [cexp][cin] (exact halving) and 0.5 * shift in fp32
+            {
+                std::vector<float> wh((size_t)b.cexp * b.cin), bh(b.cexp);
+                for (size_t j = 0; j < wh.size(); ++j) wh[j] = 0.5f * arena16src[o.t_exp + j];
+                for (int n = 0; n < b.cexp; ++n) bh[n] = 0.5f * arena[o.b_exp + n];
+                o.t_exp_h = put16(wh);
+                o.b_exp_h = put(bh);
+            }
             for (int n = 0; n < b.cexp; ++n) shift_lo_fix.push_back({o.t_aug + (size_t)n * ka + b.cin, 0.5f * arena[o.b_exp + n]});
         }
         {
@@ -952,6 +1046,12 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
             w.w_exp = A + o.w_exp; w.b_exp = A + o.b_exp;
             w.wt_exp = base16 ? base16 + o.t_exp * 2 : nullptr;
             w.wt_exp_aug = base16 ? base16 + o.t_aug * 2 : nullptr;
+            w.wt_exp_h = base16 ? base16 + o.t_exp_h * 2 : nullptr;
+            w.b_exp_h = A + o.b_exp_h;
+            if (base16 && c->k1w[i].valid) {
+                int rc = make_tmap_w(&c->tmap_w[i], w.wt_exp_h, c->blocks[i].cexp, c->blocks[i].cin, c->k1w[i].p.CC, c->precision == WHENET_PRECISION_BF16);
+                if (rc) return rc;
+            }
         }
         w.w_dw = A + o.w_dw; w.b_dw = A + o.b_dw;
         w.w_dw_h = A + o.w_dw_h; w.b_dw_h = A + o.b_dw_h;
@@ -962,6 +1062,7 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
     c->w_head = A + o_whead; c->b_head = A + o_bhead; c->wt_head = base16 ? base16 + o_thead * 2 : nullptr;
     c->w_fct = A + o_wfct; c->b_fc = A + o_bfc;
     c->weights_loaded = true;
+    c->tmaps.clear();
     drop_graphs(c);
     return 0;
 }

@@ -146,3 +146,48 @@ def test_k1p_oracle_taps(oracle32, sample_crops, jitter_crops):
             assert e < 0.12, (nm, e)
     assert np.abs(got - ref_ang).max() < 0.5
     m.close()
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_k1w_taps_vs_oracle(prec, oracle32, sample_crops, jitter_crops):
+    """K1W (k1_variant=4: weight-stationary persistent CTAs, TMA-staged input tiles, warp-specialised epilogue / depthwise):
+    depthwise outputs, SE gates and block outputs of EVERY block with an expand conv against the oracle, on an odd crop count
+    (the last two-crop item of the 7x7 blocks is half empty), plus bitwise batch invariance."""
+    import whenet_b200
+    crops = np.concatenate([sample_crops, jitter_crops[:1]])
+    m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=8)
+    m.set_option("k1_variant", 4)
+    taps = {}
+    ref_ang = np.stack(oracle32.get_angle(crops, taps), axis=1)
+    m.enable_taps(True)
+    got = np.stack(m.get_angle(crops), axis=1)
+    m.enable_taps(False)
+    lim = 0.12 if prec == "bf16" else 0.02   # rms-relative (same limits as the K1 tap test)
+    for i in range(2, 17):
+        for kind in ("dw", "gate", "block"):
+            nm = "%s%d" % (kind, i)
+            ref = taps[nm].astype(np.float64).reshape(-1)
+            g = m.tap(nm).astype(np.float64)
+            e = float(np.sqrt(((g - ref) ** 2).mean()) / (np.sqrt((ref ** 2).mean()) + 1e-30))
+            assert e < lim, (nm, e)
+    assert np.abs(got - ref_ang).max() < (0.5 if prec == "bf16" else 0.05)
+    one = np.stack(m.get_angle(crops[1:2]), axis=1)
+    assert np.array_equal(one[0], got[1])
+    big = np.concatenate([crops] * 11)[:32]
+    many = np.stack(m.get_angle(big), axis=1)
+    assert np.array_equal(many[:3], got) and np.array_equal(many[30:32], got[0:2])
+    m.close()
+
+
+def test_k1w_batch512_vs_cpu_port(bench_crops, bench_ref):
+    """K1W at the benched size and input distribution."""
+    import whenet_b200
+    m = whenet_b200.WHENet(SNAP, device=0, precision="bf16", max_batch=512)
+    m.set_option("k1_variant", 4)
+    got = np.stack(m.get_angle(bench_crops), axis=1)
+    err = np.abs(got - bench_ref).max()
+    print("K1W bf16 N=512 random uint8: max |angle - cpu port| = %.5f deg" % err)
+    assert err <= 0.6
+    m.set_option("streams", 1)
+    assert np.array_equal(np.stack(m.get_angle(bench_crops), axis=1), got)
+    m.close()

@@ -20,8 +20,8 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
 
 template <int MODE>
 __global__ void __launch_bounds__(512) probe(float* out, u64* cyc, float seed) {
-    __shared__ __align__(16) float sm[4096];
-    for (int i = threadIdx.x; i < 4096; i += 512) sm[i] = seed * (float)i;
+    __shared__ __align__(16) float sm[8192];     // 32 KB: sbase (<= 4 KB) + 3 * 4096 + 16 stays inside
+    for (int i = threadIdx.x; i < 8192; i += 512) sm[i] = seed * (float)i;
     __syncthreads();
     float v[8];
     float2 w2[8];
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(512) probe(float* out, u64* cyc, float seed) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 uint32_t a, b;
-                asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(sbase + ((it + r) & 7) * 4096));
+                asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(sbase + ((it + r) & 3) * 4096));
                 const float2 x01 = make_float2(__uint_as_float(a << 16), __uint_as_float(a & 0xffff0000u));
                 const float2 x23 = make_float2(__uint_as_float(b << 16), __uint_as_float(b & 0xffff0000u));
 #pragma unroll
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(512) probe(float* out, u64* cyc, float seed) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 uint32_t a, b;
-                asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(sbase + ((it + r) & 7) * 4096));
+                asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(sbase + ((it + r) & 3) * 4096));
                 const float x0 = __uint_as_float(a << 16), x1 = __uint_as_float(a & 0xffff0000u);
                 const float x2 = __uint_as_float(b << 16), x3 = __uint_as_float(b & 0xffff0000u);
 #pragma unroll
