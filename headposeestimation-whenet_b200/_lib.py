@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PRECISIONS = {"fp32": 0, "bf16": 1, "fp16": 2}
 
 EXPORTS = [
-    "whenet_create", "whenet_load_weights", "whenet_set_stream", "whenet_forward_u8", "whenet_forward_u8_async", "whenet_forward_f32",
+    "whenet_create", "whenet_load_weights", "whenet_export_packed", "whenet_import_packed", "whenet_set_stream", "whenet_forward_u8", "whenet_forward_u8_async", "whenet_forward_f32",
     "whenet_crop_resize_u8", "whenet_synchronize", "whenet_host_alloc", "whenet_host_free", "whenet_debug_enable_taps", "whenet_debug_tap",
     "whenet_debug_conv1x1", "whenet_debug_decode", "whenet_debug_raise_timeout", "whenet_debug_set_k1_plan", "whenet_debug_set_k1p_plan", "whenet_profile_enable", "whenet_profile_read", "whenet_launch_count", "whenet_set_option",
     "whenet_last_error", "whenet_version", "whenet_destroy",
@@ -60,6 +60,8 @@ def load():
     P = C.c_void_p
     L.whenet_create.argtypes = [C.POINTER(P), C.c_int, C.c_int, C.c_int]
     L.whenet_load_weights.argtypes = [P, C.POINTER(Tensor), C.c_int]
+    L.whenet_export_packed.argtypes = [P, P, P, P, C.POINTER(C.c_int64)]
+    L.whenet_import_packed.argtypes = [P, P, C.c_int64, P, C.c_int64, P, C.c_int64]
     L.whenet_set_stream.argtypes = [P, P]
     L.whenet_forward_u8.argtypes = [P, P, C.c_int, C.c_int, P, P, C.c_int]
     L.whenet_forward_f32.argtypes = [P, P, C.c_int, C.c_int, P, P, C.c_int]

@@ -165,6 +165,7 @@ struct whenet_ctx {
     std::vector<BlockW> bw;
     float* d_arena = nullptr;
     void* d_arena16 = nullptr;
+    std::vector<int64_t> layout;   // offsets of every packed tensor inside the two arenas (the persisted artefact's index)
     float *w_stem = nullptr, *b_stem = nullptr, *lut = nullptr;
     float *w_head = nullptr, *b_head = nullptr, *w_fct = nullptr, *b_fc = nullptr;
     void* wt_head = nullptr;
@@ -783,6 +784,67 @@ template <typename T16> T16 to16(float v);
 template <> __nv_bfloat16 to16<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 template <> __half to16<__half>(float v) { return __float2half_rn(v); }
 
+constexpr int64_t kPackMagic = 0x57484e3242323030LL;   // "WHN2B200"
+constexpr int64_t kPackVersion = 2;
+constexpr int kPackHeader = 14, kPackPerBlock = 17;
+
+// Upload a packed weight image (fp32 arena + 16-bit arena + index) and point the context at it.  Shared by
+// whenet_load_weights (which has just built the image from the raw Keras tensors) and whenet_import_packed (which read it
+// from the persisted artefact): folding, transposition and rounding are NOT repeated on import.
+int bind_packed(whenet_ctx* c, const float* arena, size_t n_f32, const uint16_t* h16, size_t n_16, const std::vector<int64_t>& L) {
+    const size_t nb = c->blocks.size();
+    if (L.size() != (size_t)kPackHeader + nb * kPackPerBlock || L[0] != kPackMagic || L[1] != kPackVersion)
+        return fail(WHENET_ESHAPE, "packed weights: bad index (size %zu, magic/version mismatch)", L.size());
+    if (L[2] != c->precision) return fail(WHENET_ESHAPE, "packed weights were exported for precision %lld, this context is %d", (long long)L[2], c->precision);
+    if ((size_t)L[3] != n_f32 || (size_t)L[4] != n_16 || (size_t)L[13] != nb) return fail(WHENET_ESHAPE, "packed weights: arena sizes do not match the index");
+    if ((c->precision != WHENET_PRECISION_FP32) != (n_16 > 0)) return fail(WHENET_ESHAPE, "packed weights: 16-bit arena does not fit the precision");
+    for (size_t i = 5; i < L.size(); ++i)
+        if (i != 13 && (L[i] < 0 || (size_t)L[i] >= std::max(n_f32, n_16))) return fail(WHENET_ESHAPE, "packed weights: offset %zu out of range", i);
+    if (c->d_arena) { cudaFree(c->d_arena); c->d_arena = nullptr; }
+    if (c->d_arena16) { cudaFree(c->d_arena16); c->d_arena16 = nullptr; }
+    CK(cudaMalloc(&c->d_arena, n_f32 * sizeof(float)));
+    CK(cudaMemcpy(c->d_arena, arena, n_f32 * sizeof(float), cudaMemcpyHostToDevice));
+    char* base16 = nullptr;
+    if (n_16) {
+        CK(cudaMalloc(&c->d_arena16, n_16 * 2 + 256));
+        CK(cudaMemcpy(c->d_arena16, h16, n_16 * 2, cudaMemcpyHostToDevice));
+        base16 = (char*)c->d_arena16;
+    }
+    float* A = c->d_arena;
+    c->w_stem = A + L[5]; c->b_stem = A + L[6]; c->lut = A + L[7];
+    if ((size_t)L[5] + 27 * 32 > n_f32 || (size_t)L[6] + 32 > n_f32) return fail(WHENET_ESHAPE, "packed weights: stem out of range");
+    memcpy(c->stem_params.w, arena + L[5], sizeof(c->stem_params.w));
+    memcpy(c->stem_params.b, arena + L[6], sizeof(c->stem_params.b));
+    c->w_head = A + L[8]; c->b_head = A + L[9]; c->wt_head = base16 ? base16 + L[10] * 2 : nullptr;
+    c->w_fct = A + L[11]; c->b_fc = A + L[12];
+    for (size_t i = 0; i < nb; ++i) {
+        const int64_t* o = &L[kPackHeader + i * kPackPerBlock];
+        BlockW& w = c->bw[i];
+        w = BlockW{};
+        if (c->blocks[i].has_expand) {
+            w.w_exp = A + o[0]; w.b_exp = A + o[1];
+            w.wt_exp = base16 ? base16 + o[10] * 2 : nullptr;
+            w.wt_exp_aug = base16 ? base16 + o[12] * 2 : nullptr;
+            w.wt_exp_h = base16 ? base16 + o[15] * 2 : nullptr;
+            w.b_exp_h = A + o[16];
+            if (base16 && c->k1w[i].valid) {
+                int rc = make_tmap_w(&c->tmap_w[i], w.wt_exp_h, c->blocks[i].cexp, c->blocks[i].cin, c->k1w[i].p.CC, c->precision == WHENET_PRECISION_BF16);
+                if (rc) return rc;
+            }
+        }
+        w.w_dw = A + o[2]; w.b_dw = A + o[3];
+        w.w_se1t = A + o[4]; w.b_se1 = A + o[5]; w.w_se2 = A + o[6]; w.b_se2 = A + o[7];
+        w.w_proj = A + o[8]; w.b_proj = A + o[9];
+        w.wt_proj = base16 ? base16 + o[11] * 2 : nullptr;
+        w.w_dw_h = A + o[13]; w.b_dw_h = A + o[14];
+    }
+    c->layout = L;
+    c->weights_loaded = true;
+    c->tmaps.clear();
+    drop_graphs(c);
+    return 0;
+}
+
 }  // namespace
 
 // ============================================================================= C ABI
@@ -934,8 +996,6 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
         for (int ch = 0; ch < 3; ++ch)
             for (int v = 0; v < 256; ++v) lut[ch * 256 + v] = (float)((((double)v / 255.0) - mean[ch]) / sd[ch]);
         o_wstem = put(w); o_bstem = put(b); o_lut = put(lut);
-        memcpy(c->stem_params.w, w.data(), sizeof(c->stem_params.w));
-        memcpy(c->stem_params.b, b.data(), sizeof(c->stem_params.b));
     }
     // ---- 16 MBConv blocks
     for (size_t i = 0; i < c->blocks.size(); ++i) {
@@ -1013,14 +1073,10 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
     if (conv != 65 || dwc != 16 || bn != 49)
         return fail(WHENET_ESHAPE, "consumed %d/%d/%d conv/dw/bn layers, expected 65/16/49", conv, dwc, bn);
 
-    // ---- upload
-    if (c->d_arena) { cudaFree(c->d_arena); c->d_arena = nullptr; }
-    if (c->d_arena16) { cudaFree(c->d_arena16); c->d_arena16 = nullptr; }
-    CK(cudaMalloc(&c->d_arena, arena.size() * sizeof(float)));
-    CK(cudaMemcpy(c->d_arena, arena.data(), arena.size() * sizeof(float), cudaMemcpyHostToDevice));
-    char* base16 = nullptr;
+    // ---- 16-bit arena in the storage type of this context
+    std::vector<uint16_t> h16;
     if (c->precision != WHENET_PRECISION_FP32) {
-        std::vector<uint16_t> h16(arena16src.size());
+        h16.resize(arena16src.size());
         for (size_t i = 0; i < h16.size(); ++i) {
             if (c->precision == WHENET_PRECISION_BF16) { __nv_bfloat16 v = to16<__nv_bfloat16>(arena16src[i]); memcpy(&h16[i], &v, 2); }
             else { __half v = to16<__half>(arena16src[i]); memcpy(&h16[i], &v, 2); }
@@ -1033,38 +1089,37 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
             else { __half v; memcpy(&v, &h16[fx.first], 2); hi = __half2float(v);
                    __half lo = __float2half_rn(fx.second - hi); memcpy(&h16[fx.first + 1], &lo, 2); }
         }
-        CK(cudaMalloc(&c->d_arena16, h16.size() * 2 + 256));
-        CK(cudaMemcpy(c->d_arena16, h16.data(), h16.size() * 2, cudaMemcpyHostToDevice));
-        base16 = (char*)c->d_arena16;
     }
-    float* A = c->d_arena;
-    c->w_stem = A + o_wstem; c->b_stem = A + o_bstem; c->lut = A + o_lut;
+    // ---- the index of the packed image: everything bind_packed needs to find a tensor again
+    std::vector<int64_t> layout = {kPackMagic, kPackVersion, c->precision, (int64_t)arena.size(), (int64_t)h16.size(),
+                                   (int64_t)o_wstem, (int64_t)o_bstem, (int64_t)o_lut, (int64_t)o_whead, (int64_t)o_bhead, (int64_t)o_thead,
+                                   (int64_t)o_wfct, (int64_t)o_bfc, (int64_t)c->blocks.size()};
     for (size_t i = 0; i < c->blocks.size(); ++i) {
         const Off& o = offs[i];
-        BlockW& w = c->bw[i];
-        if (c->blocks[i].has_expand) {
-            w.w_exp = A + o.w_exp; w.b_exp = A + o.b_exp;
-            w.wt_exp = base16 ? base16 + o.t_exp * 2 : nullptr;
-            w.wt_exp_aug = base16 ? base16 + o.t_aug * 2 : nullptr;
-            w.wt_exp_h = base16 ? base16 + o.t_exp_h * 2 : nullptr;
-            w.b_exp_h = A + o.b_exp_h;
-            if (base16 && c->k1w[i].valid) {
-                int rc = make_tmap_w(&c->tmap_w[i], w.wt_exp_h, c->blocks[i].cexp, c->blocks[i].cin, c->k1w[i].p.CC, c->precision == WHENET_PRECISION_BF16);
-                if (rc) return rc;
-            }
-        }
-        w.w_dw = A + o.w_dw; w.b_dw = A + o.b_dw;
-        w.w_dw_h = A + o.w_dw_h; w.b_dw_h = A + o.b_dw_h;
-        w.w_se1t = A + o.w_se1t; w.b_se1 = A + o.b_se1; w.w_se2 = A + o.w_se2; w.b_se2 = A + o.b_se2;
-        w.w_proj = A + o.w_proj; w.b_proj = A + o.b_proj;
-        w.wt_proj = base16 ? base16 + o.t_proj * 2 : nullptr;
+        const bool e = c->blocks[i].has_expand;
+        for (size_t v : {e ? o.w_exp : 0, e ? o.b_exp : 0, o.w_dw, o.b_dw, o.w_se1t, o.b_se1, o.w_se2, o.b_se2, o.w_proj, o.b_proj, e ? o.t_exp : 0, o.t_proj,
+                         e ? o.t_aug : 0, o.w_dw_h, o.b_dw_h, e ? o.t_exp_h : 0, e ? o.b_exp_h : 0})
+            layout.push_back((int64_t)v);
     }
-    c->w_head = A + o_whead; c->b_head = A + o_bhead; c->wt_head = base16 ? base16 + o_thead * 2 : nullptr;
-    c->w_fct = A + o_wfct; c->b_fc = A + o_bfc;
-    c->weights_loaded = true;
-    c->tmaps.clear();
-    drop_graphs(c);
+    return bind_packed(c, arena.data(), arena.size(), h16.data(), h16.size(), layout);
+}
+
+
+int whenet_export_packed(whenet_ctx* c, float* arena_f32, uint16_t* arena_16, int64_t* index, int64_t sizes[3]) {
+    if (!c || !sizes) return fail(WHENET_EINVAL, "bad arguments");
+    if (!c->weights_loaded) return fail(WHENET_ENOWEIGHTS, "no weights loaded");
+    sizes[0] = c->layout[3]; sizes[1] = c->layout[4]; sizes[2] = (int64_t)c->layout.size();
+    CK(cudaSetDevice(c->device));
+    if (arena_f32) CK(cudaMemcpy(arena_f32, c->d_arena, (size_t)sizes[0] * sizeof(float), cudaMemcpyDeviceToHost));
+    if (arena_16 && sizes[1]) CK(cudaMemcpy(arena_16, c->d_arena16, (size_t)sizes[1] * 2, cudaMemcpyDeviceToHost));
+    if (index) memcpy(index, c->layout.data(), c->layout.size() * sizeof(int64_t));
     return 0;
+}
+
+int whenet_import_packed(whenet_ctx* c, const float* arena_f32, int64_t n_f32, const uint16_t* arena_16, int64_t n_16, const int64_t* index, int64_t n_index) {
+    if (!c || !arena_f32 || !index || n_f32 < 1 || n_16 < 0 || n_index < 1 || (n_16 > 0 && !arena_16)) return fail(WHENET_EINVAL, "bad arguments");
+    CK(cudaSetDevice(c->device));
+    return bind_packed(c, arena_f32, (size_t)n_f32, arena_16, (size_t)n_16, std::vector<int64_t>(index, index + n_index));
 }
 
 int whenet_set_stream(whenet_ctx* c, void* s) {

@@ -11,7 +11,7 @@ from typing import Dict, Tuple
 
 import numpy as np
 
-_DTYPES = {"F32": np.dtype("<f4"), "F16": np.dtype("<f2"), "U8": np.dtype("u1"), "I32": np.dtype("<i4"), "I64": np.dtype("<i8")}
+_DTYPES = {"F32": np.dtype("<f4"), "F16": np.dtype("<f2"), "U8": np.dtype("u1"), "U16": np.dtype("<u2"), "I32": np.dtype("<i4"), "I64": np.dtype("<i8")}
 _NAMES = {v: k for k, v in _DTYPES.items()}
 
 

@@ -106,7 +106,14 @@ class WHENet:
         self.idx_tensor_yaw = np.array([idx for idx in range(120)], dtype=np.float32)
 
     # ------------------------------------------------------------------ plumbing
+    PACKED_FORMAT = "whenet-b200-packed-v2"
+
     def _load(self, snapshot):
+        if snapshot is not None and os.fspath(snapshot).endswith(".safetensors"):
+            from . import stlite
+            z, meta = stlite.load(os.fspath(snapshot)) if os.path.exists(os.fspath(snapshot)) else (None, {})
+            if z is not None and meta.get("format") == self.PACKED_FORMAT:
+                return self._import_packed(z, meta)
         _names, w = _weights.load_snapshot(snapshot)
         arr = (_lib.Tensor * len(w))()
         keep = []
@@ -119,6 +126,29 @@ class WHENet:
             for d in range(a.ndim):
                 arr[i].dims[d] = a.shape[d]
         check(self._L.whenet_load_weights(self._h, arr, len(w)))
+
+    def _import_packed(self, z, meta):
+        """The device image exported by ``export_packed``: BN already folded, kernels already transposed / rounded to the
+        storage type - uploaded as is (replaces the HDF5 walk + fold + repack of reference whenet.py:15-16)."""
+        if meta.get("precision") != self.precision:
+            raise ValueError("packed weights were exported for precision %r, this model is %r" % (meta.get("precision"), self.precision))
+        a32 = np.ascontiguousarray(z["arena_f32"], dtype=np.float32)
+        a16 = np.ascontiguousarray(z["arena_16"], dtype=np.uint16)
+        idx = np.ascontiguousarray(z["index"], dtype=np.int64)
+        check(self._L.whenet_import_packed(self._h, _ptr(a32), a32.size, _ptr(a16) if a16.size else None, a16.size, _ptr(idx), idx.size))
+
+    def export_packed(self, path):
+        """Persist the packed device image of the loaded weights (fp32 arena, 16-bit arena in this model's storage type,
+        index) as one .safetensors file; ``WHENet(path, precision=<same>)`` loads it without touching the Keras tensors."""
+        from . import stlite
+        sizes = (C.c_int64 * 3)()
+        check(self._L.whenet_export_packed(self._h, None, None, None, sizes))
+        a32 = np.empty((sizes[0],), np.float32)
+        a16 = np.empty((sizes[1],), np.uint16)
+        idx = np.empty((sizes[2],), np.int64)
+        check(self._L.whenet_export_packed(self._h, _ptr(a32), _ptr(a16) if a16.size else None, _ptr(idx), sizes))
+        stlite.save(path, {"arena_f32": a32, "arena_16": a16, "index": idx},
+                    {"format": self.PACKED_FORMAT, "precision": self.precision, "library": self._L.whenet_version().decode()})
 
     @staticmethod
     def _check_shape(x):

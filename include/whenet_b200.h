@@ -73,6 +73,15 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision);
  * preceding conv, re-lays weights out for the kernels and uploads them. */
 int whenet_load_weights(whenet_ctx* ctx, const whenet_tensor* tensors, int n_tensors);
 
+/* Persisted packed artefact: the device image whenet_load_weights built - BatchNorm folded, 1x1 kernels
+ * transposed to K-major and rounded to the context's storage type, K1 constants pre-halved - as two flat arenas plus an
+ * index of offsets.  Export: call with NULL buffers to get sizes[3] = {fp32 elements, 16-bit elements, index entries}, then
+ * with buffers of those sizes.  Import replaces whenet_load_weights (reference whenet.py:15-16) for a context of the SAME
+ * precision: no HDF5 walk, no folding, no repacking - one validation pass over the index and two uploads. */
+int whenet_export_packed(whenet_ctx* ctx, float* arena_f32, uint16_t* arena_16, int64_t* index, int64_t sizes[3]);
+int whenet_import_packed(whenet_ctx* ctx, const float* arena_f32, int64_t n_f32, const uint16_t* arena_16, int64_t n_16,
+                         const int64_t* index, int64_t n_index);
+
 /* Run on an existing CUDA stream (cudaStream_t / CUstream) instead of the
  * context's own; NULL restores the internal stream. */
 int whenet_set_stream(whenet_ctx* ctx, void* cuda_stream);

@@ -191,3 +191,40 @@ def test_k1w_batch512_vs_cpu_port(bench_crops, bench_ref):
     m.set_option("streams", 1)
     assert np.array_equal(np.stack(m.get_angle(bench_crops), axis=1), got)
     m.close()
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_packed_artefact_round_trip(prec, tmp_path, sample_crops, jitter_crops):
+    """export the packed device image (BN-folded, tiled, storage-typed), construct a model from it, get
+    bit-identical angles; the artefact is precision-specific and a damaged index is refused."""
+    import time
+    import whenet_b200
+    from whenet_b200 import stlite
+    crops = np.concatenate([sample_crops, jitter_crops])
+    t0 = time.perf_counter()
+    a = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=8)
+    t_raw = time.perf_counter() - t0
+    ref = np.stack(a.get_angle(crops), axis=1)
+    path = str(tmp_path / ("whenet_%s.packed.safetensors" % prec))
+    a.export_packed(path)
+    a.close()
+    t0 = time.perf_counter()
+    b = whenet_b200.WHENet(path, device=0, precision=prec, max_batch=8)
+    t_packed = time.perf_counter() - t0
+    print("%s constructor: raw npz %.3f s, packed artefact %.3f s" % (prec, t_raw, t_packed))
+    got = np.stack(b.get_angle(crops), axis=1)
+    assert np.array_equal(got, ref)
+    if prec == "bf16":
+        b.set_option("k1_variant", 4)                      # the TMA weight maps were rebuilt on import
+        assert np.abs(np.stack(b.get_angle(crops), axis=1) - ref).max() < 0.3
+    b.close()
+    other = "fp32" if prec == "bf16" else "bf16"
+    with pytest.raises((ValueError, whenet_b200.WhenetError)):
+        whenet_b200.WHENet(path, device=0, precision=other, max_batch=8)
+    z, meta = stlite.load(path)
+    idx = z["index"].copy()
+    idx[20] = 1 << 40
+    bad = str(tmp_path / "bad.safetensors")
+    stlite.save(bad, {"arena_f32": z["arena_f32"], "arena_16": z["arena_16"], "index": idx}, meta)
+    with pytest.raises(whenet_b200.WhenetError):
+        whenet_b200.WHENet(bad, device=0, precision=prec, max_batch=8)
