@@ -42,6 +42,7 @@ struct alignas(64) K1WParams {
     void* out;             // T [N][Ho][Ho][Cexp]
     float* partial;        // [N][tiles][Cexp]
     int* tflag;            // mbarrier-timeout flag (mapped pinned host memory)
+    long long* trace;      // NULL, or [grid][16] cycle counters: where each role of each CTA waited (tools/k1w_trace.py)
     int Hin, Ho, Cin, Cexp, pad;
     int TH, TW, IH, IW, tiles_x, tiles;
     int NB;                // crops per item (> 1 only when one tile is the whole image)
@@ -67,39 +68,54 @@ struct alignas(64) K1WParams {
 
 namespace k1w {
 
-// Bounded wait.  try_wait gets a suspend-time hint (ns): the warp sleeps in hardware until the phase completes instead of
-// re-polling every ~150 cycles - ncu showed the re-poll loop of K1P at 22 % of all issued instructions, stolen from the
-// warps that had work.  256 x 4 ms bounds a protocol bug to about a second; then the flag is raised and every role of the
-// CTA falls through its remaining waits.
-__device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int* tflag) {
-    if (*abort_flag) return;
-    const uint32_t addr = tc::smem_u32(bar);
-    for (uint32_t it = 0; it < 256u; ++it) {
+// Bounded wait on a barrier given by its shared-memory address.  The loop body is try_wait + branch (ncu showed the
+// re-poll loop of the first version at 16-22 % of all issued instructions, taken from the warps that had work); the abort
+// flag is looked at every 64 polls only.  A protocol bug ends in the timeout flag instead of a hung GPU.
+__device__ __forceinline__ void wait(uint32_t bar_addr, uint32_t parity, volatile int* abort_flag, int* tflag) {
+    for (uint32_t outer = 0; outer < (1u << 16); ++outer) {
         uint32_t done;
         asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+            "mov.u32 n, 64;\n"
+            "K1W_POLL_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 1000000;\n\t"
+            "@p bra K1W_DONE_%=;\n\t"
+            "sub.u32 n, n, 1;\n\t"
+            "setp.ne.u32 p, n, 0;\n\t"
+            "@p bra K1W_POLL_%=;\n\t"
+            "setp.eq.u32 p, n, 1;\n"          // false: n == 0 here
+            "K1W_DONE_%=:\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity), "r"(4000000u) : "memory");
+            : "=r"(done) : "r"(bar_addr), "r"(parity) : "memory");
         if (done) return;
         if (*abort_flag) return;
     }
     *abort_flag = 1;
     *reinterpret_cast<volatile int*>(tflag) = 1;
 }
-__device__ __forceinline__ void arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+// the same with the cycles spent waiting added to `acc` (trace builds of the roles' lane 0)
+__device__ __forceinline__ void wait_t(uint32_t bar_addr, uint32_t parity, volatile int* abort_flag, int* tflag, bool tr, long long& acc) {
+    if (!tr) { wait(bar_addr, parity, abort_flag, tflag); return; }
+    const long long t0 = clock64();
+    wait(bar_addr, parity, abort_flag, tflag);
+    acc += clock64() - t0;
 }
-__device__ __forceinline__ void arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void arrive(uint32_t bar_addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
-__device__ __forceinline__ void tma_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
+__device__ __forceinline__ void arrive_expect_tx(uint32_t bar_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void commit(uint32_t bar_addr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void tma_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar_addr) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(tc::smem_u32(bar)) : "memory");
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar_addr) : "memory");
 }
-__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar_addr) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(tc::smem_u32(bar)) : "memory");
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar_addr) : "memory");
 }
 // two fp32 adds in one instruction
 __device__ __forceinline__ float2 fadd2(const float2& a, const float2& b) {
@@ -123,10 +139,25 @@ constexpr int kCtrlThreads = 128;      // warps 0-3: TMA producer, MMA issuer, t
                                        // warp whose index is a multiple of 4: TMEM lane quadrant = warp & 3)
 }  // namespace k1w
 
+// Items of one CTA: item = group + k * groups, decomposed into (crop block q, tile t) without a division per step.
+struct ItemIter {
+    int item, q, t, dq, dt, tiles, step;
+    __device__ __forceinline__ void init(int group, int groups, int tiles_) {
+        tiles = tiles_; step = groups; item = group;
+        q = group / tiles_; t = group - q * tiles_;
+        dq = groups / tiles_; dt = groups - dq * tiles_;
+    }
+    __device__ __forceinline__ void next() {
+        item += step; q += dq; t += dt;
+        if (t >= tiles) { t -= tiles; ++q; }
+    }
+};
+
 template <typename T, int KS, int S, int R, int NT>
 __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_a_full[2], bar_a_empty[2], bar_t_full[2], bar_t_empty[2], bar_e_full[2], bar_e_empty[2], bar_w;
+    // [0,1] a_full  [2,3] a_empty  [4,5] t_full  [6,7] t_empty  [8,9] e_full  [10,11] e_empty  [12] w
+    __shared__ __align__(8) uint64_t bars[13];
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_abort_mem;
     volatile int* s_abort = &s_abort_mem;
@@ -134,21 +165,27 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = smem0, sW = smem0 + p.off_w, sC = smem0 + p.off_c, sE = smem0 + p.off_e, sR = smem0 + p.off_r;
+    const uint32_t bar0 = tc::smem_u32(&bars[0]);
+    const uint32_t b_a_full = bar0, b_a_empty = bar0 + 16, b_t_full = bar0 + 32, b_t_empty = bar0 + 48, b_e_full = bar0 + 64,
+                   b_e_empty = bar0 + 80, b_w = bar0 + 96;
     const int CC = p.CC, pitchE = p.pitchE;
     const int chunk = blockIdx.x % p.n_chunks, group = blockIdx.x / p.n_chunks;
     const int cbase = chunk * CC;
     const int n_epi_threads = 32 * p.n_epi;
+    const bool tr = p.trace != nullptr && lane == 0;
+    long long tw0 = 0, tw1 = 0;                          // trace: cycles this thread spent in its waits
+    const long long t_begin = tr ? clock64() : 0;
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&bar_a_full[i], 1);
-            tc::mbar_init(&bar_a_empty[i], 1);
-            tc::mbar_init(&bar_t_full[i], 1);
-            tc::mbar_init(&bar_t_empty[i], n_epi_threads);
-            tc::mbar_init(&bar_e_full[i], n_epi_threads);
-            tc::mbar_init(&bar_e_empty[i], p.n_dw);
+            tc::mbar_init(&bars[0 + i], 1);
+            tc::mbar_init(&bars[2 + i], 1);
+            tc::mbar_init(&bars[4 + i], 1);
+            tc::mbar_init(&bars[6 + i], n_epi_threads);
+            tc::mbar_init(&bars[8 + i], n_epi_threads);
+            tc::mbar_init(&bars[10 + i], p.n_dw);
         }
-        tc::mbar_init(&bar_w, 1);
+        tc::mbar_init(&bars[12], 1);
         s_abort_mem = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -161,21 +198,9 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem_base;
 
-    // item -> geometry.  An item is (crop n0 .. n0+NB-1, output tile): origin of the output tile and of its input halo tile.
-    const float inv_tiles = 1.0f / (float)p.tiles, inv_tx = 1.0f / (float)p.tiles_x;
-    struct Geo { int n0, tile, ty0, tx0, iy0, ix0; };
-    auto geom = [&](int item) {
-        Geo g;
-        const int q = div_small(item, inv_tiles);
-        g.n0 = q * p.NB;
-        g.tile = item - q * p.tiles;
-        const int tyi = div_small(g.tile, inv_tx);
-        g.ty0 = tyi * p.TH;
-        g.tx0 = (g.tile - tyi * p.tiles_x) * p.TW;
-        g.iy0 = g.ty0 * S - p.pad;
-        g.ix0 = g.tx0 * S - p.pad;
-        return g;
-    };
+    const float inv_tx = 1.0f / (float)p.tiles_x;
+    ItemIter it;
+    it.init(group, p.groups, p.tiles);
 
     if (warp == 0) {
         // =========================================================================== TMA producer
@@ -183,29 +208,28 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
             asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW) : "memory");
             // this CTA's slice of the expand weights: resident for the whole launch
-            k1w::arrive_expect_tx(&bar_w, p.w_tx);
-            for (int kb = 0; kb < p.nkb; ++kb) k1w::tma_2d(sW + (uint32_t)kb * CC * 128, &p.tmW, kb * 64, cbase, &bar_w);
-            int k = 0;
-            for (int item = group; item < p.items; item += p.groups, ++k) {
-                const Geo g = geom(item);
+            k1w::arrive_expect_tx(b_w, p.w_tx);
+            for (int kb = 0; kb < p.nkb; ++kb) k1w::tma_2d(sW + (uint32_t)kb * CC * 128, &p.tmW, kb * 64, cbase, b_w);
+            for (int k = 0; it.item < p.items; it.next(), ++k) {
+                const int tyi = div_small(it.t, inv_tx);
+                const int iy0 = tyi * p.TH * S - p.pad, ix0 = (it.t - tyi * p.tiles_x) * p.TW * S - p.pad;
                 const int st = p.NA == 2 ? (k & 1) : 0;
                 const uint32_t par = p.NA == 2 ? ((k >> 1) & 1) : (k & 1);
-                k1w::wait(&bar_a_empty[st], par ^ 1, s_abort, p.tflag);         // the MMAs that read this stage have completed
-                k1w::arrive_expect_tx(&bar_a_full[st], p.a_tx);
+                k1w::wait_t(b_a_empty + 8 * st, par ^ 1, s_abort, p.tflag, tr, tw0);         // the MMAs that read this stage have completed
+                k1w::arrive_expect_tx(b_a_full + 8 * st, p.a_tx);
                 for (int kb = 0; kb < p.nkb; ++kb)
-                    k1w::tma_4d(sA + (uint32_t)st * p.a_stage + (uint32_t)kb * p.rows_alloc * 128, &p.tmA, kb * 64, g.ix0, g.iy0, g.n0, &bar_a_full[st]);
+                    k1w::tma_4d(sA + (uint32_t)st * p.a_stage + (uint32_t)kb * p.rows_alloc * 128, &p.tmA, kb * 64, ix0, iy0, it.q * p.NB, b_a_full + 8 * st);
             }
         }
     } else if (warp == 1) {
         // =========================================================================== MMA issuer
-        k1w::wait(&bar_w, 0, s_abort, p.tflag);
-        int k = 0;
-        for (int item = group; item < p.items; item += p.groups, ++k) {
+        k1w::wait(b_w, 0, s_abort, p.tflag);
+        for (int k = 0; it.item < p.items; it.next(), ++k) {
             const int st = p.NA == 2 ? (k & 1) : 0;
             const uint32_t par = p.NA == 2 ? ((k >> 1) & 1) : (k & 1);
             const int tb = k & 1;
-            k1w::wait(&bar_a_full[st], par, s_abort, p.tflag);
-            k1w::wait(&bar_t_empty[tb], ((k >> 1) & 1) ^ 1, s_abort, p.tflag);  // the epilogue has drained this accumulator
+            k1w::wait_t(b_a_full + 8 * st, par, s_abort, p.tflag, tr, tw0);
+            k1w::wait_t(b_t_empty + 8 * tb, ((k >> 1) & 1) ^ 1, s_abort, p.tflag, tr, tw1);  // the epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0 && !*s_abort) {
                 const uint32_t a0 = sA + (uint32_t)st * p.a_stage;
@@ -217,8 +241,8 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
                         tc::umma_f16(tmem_base + (uint32_t)(tb * p.tbuf_cols + mt * CC), ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2),
                                      p.idesc, ks ? 1u : 0u);
                     }
-                tc::umma_commit(&bar_t_full[tb]);
-                tc::umma_commit(&bar_a_empty[st]);
+                k1w::commit(b_t_full + 8 * tb);
+                k1w::commit(b_a_empty + 8 * st);
             }
             __syncwarp();
         }
@@ -228,7 +252,6 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
         const int grp = (warp - 4) >> 2, NG = p.n_epi >> 2;
         const int units = CC >> 4;
         const int npix = p.IH * p.IW;
-        const float inv_IW = 1.0f / (float)p.IW, inv_npix = 1.0f / (float)npix;
         const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
         // BN shifts of this CTA's channels -> shared memory (read by this group only; published by a group barrier)
         {
@@ -236,47 +259,48 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
             for (int c = tid - k1w::kCtrlThreads; c < CC; c += n_epi_threads) sh[c] = p.shift[cbase + c];
             asm volatile("bar.sync 2, %0;" ::"r"(n_epi_threads) : "memory");
         }
-        int k = 0;
-        for (int item = group; item < p.items; item += p.groups, ++k) {
-            const Geo g = geom(item);
-            const int buf = k & 1;
-            // rows of this thread: r = mt * 128 + q4 * 32 + lane.  In range (part of the box) / inside the image?
-            bool in_box[3], in_img[3];
+        // rows of this thread: r = mt * 128 + q4 * 32 + lane.  Their crop / position inside the halo tile and their E row
+        // do not depend on the item; only the tile origin does.
+        int r_ty[3], r_tx[3], r_j[3];
+        uint32_t r_e[3];
+        bool in_box[3];
+        {
+            const float inv_IW = 1.0f / (float)p.IW, inv_npix = 1.0f / (float)npix;
 #pragma unroll
             for (int mt = 0; mt < 3; ++mt) {
                 const int r = mt * BM + q4 * 32 + lane;
-                in_box[mt] = r < p.rows;
+                in_box[mt] = mt < p.mtiles && r < p.rows;
                 const int rc = in_box[mt] ? r : 0;
-                const int j = p.NB == 1 ? 0 : div_small(rc, inv_npix);
-                const int q = rc - j * npix;
-                const int ty = div_small(q, inv_IW), tx = q - ty * p.IW;
-                const int iy = g.iy0 + ty, ix = g.ix0 + tx;
-                in_img[mt] = in_box[mt] && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Hin && g.n0 + j < p.N;
+                r_j[mt] = p.NB == 1 ? 0 : div_small(rc, inv_npix);
+                const int q = rc - r_j[mt] * npix;
+                r_ty[mt] = div_small(q, inv_IW);
+                r_tx[mt] = q - r_ty[mt] * p.IW;
+                r_e[mt] = (uint32_t)(r_j[mt] * p.e_rows + q) * pitchE;
             }
-            int mt_count = 0;
+        }
+        int mt_count = 0;
 #pragma unroll
-            for (int mt = 0; mt < 3; ++mt) mt_count += (mt < p.mtiles && mt * BM + q4 * 32 < p.rows) ? 1 : 0;   // a prefix of the tiles
-            const int n_pairs = mt_count * units;
-            k1w::wait(&bar_t_full[buf], (k >> 1) & 1, s_abort, p.tflag);
-            k1w::wait(&bar_e_empty[buf], ((k >> 1) & 1) ^ 1, s_abort, p.tflag);     // the depthwise of item k-2 is done with this E
+        for (int mt = 0; mt < 3; ++mt) mt_count += (mt < p.mtiles && mt * BM + q4 * 32 < p.rows) ? 1 : 0;   // a prefix of the tiles
+        const uint32_t t_q = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        for (int k = 0; it.item < p.items; it.next(), ++k) {
+            const int tyi = div_small(it.t, inv_tx);
+            const int iy0 = tyi * p.TH * S - p.pad, ix0 = (it.t - tyi * p.tiles_x) * p.TW * S - p.pad, n0 = it.q * p.NB;
+            const int buf = k & 1;
+            bool in_img[3];
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt)
+                in_img[mt] = in_box[mt] && (unsigned)(iy0 + r_ty[mt]) < (unsigned)p.Hin && (unsigned)(ix0 + r_tx[mt]) < (unsigned)p.Hin && n0 + r_j[mt] < p.N;
+            k1w::wait_t(b_t_full + 8 * buf, (k >> 1) & 1, s_abort, p.tflag, tr, tw0);
+            k1w::wait_t(b_e_empty + 8 * buf, ((k >> 1) & 1) ^ 1, s_abort, p.tflag, tr, tw1);     // the depthwise of item k-2 is done with this E
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (!*s_abort) {
-                // E rows of the NB crops are e_rows apart; row r of the box belongs to crop r / npix
                 const uint32_t e0 = sE + (uint32_t)buf * p.e_buf;
-                const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * p.tbuf_cols);
-                auto e_addr = [&](int mt) {
-                    const int r = mt * BM + q4 * 32 + lane;
-                    if (p.NB == 1) return e0 + (uint32_t)r * pitchE;
-                    const int j = div_small(r < p.rows ? r : 0, inv_npix);
-                    return e0 + (uint32_t)(j * p.e_rows + (r - j * npix)) * pitchE;
-                };
-                const uint32_t ea[3] = {e_addr(0), e_addr(1), e_addr(2)};
-                auto col_of = [&](int f) { const int mt = f >= 2 * units ? 2 : (f >= units ? 1 : 0); return (uint32_t)(mt * CC + (f - mt * units) * 16); };
-                auto process = [&](uint32_t (&r)[16], int f) {
-                    const int mt = f >= 2 * units ? 2 : (f >= units ? 1 : 0), u = f - mt * units;
+                const uint32_t t0 = t_q + (uint32_t)(buf * p.tbuf_cols);
+                // (M tile, 16-column unit) pairs of this warp: f = grp, grp + NG, ... ; f -> (mt, u) advances without a division
+                auto process = [&](uint32_t (&r)[16], int mt, int u) {
                     const bool box = mt == 0 ? in_box[0] : (mt == 1 ? in_box[1] : in_box[2]);
                     const bool img = mt == 0 ? in_img[0] : (mt == 1 ? in_img[1] : in_img[2]);
-                    const uint32_t dst = (mt == 0 ? ea[0] : (mt == 1 ? ea[1] : ea[2])) + u * 32;
+                    const uint32_t dst = e0 + (mt == 0 ? r_e[0] : (mt == 1 ? r_e[1] : r_e[2])) + u * 32;
                     if (img) {
                         uint32_t o[8];
 #pragma unroll
@@ -296,24 +320,27 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
                     }
                 };
                 uint32_t ra[16], rb[16];
-                int f = grp;
-                if (f < n_pairs) tmem_ld16_issue(t0 + col_of(f), ra);
-                while (f < n_pairs) {
+                int mt = 0, u = grp;
+                if (u >= units) { u -= units; ++mt; }                  // NG <= 2: at most one wrap
+                auto advance = [&](int& m, int& uu) { uu += NG; if (uu >= units) { uu -= units; ++m; } };
+                if (mt < mt_count) tmem_ld16_issue(t0 + (uint32_t)(mt * CC + u * 16), ra);
+                while (mt < mt_count) {
                     tmem_ld16_wait(ra);
-                    const int f2 = f + NG;
-                    if (f2 < n_pairs) tmem_ld16_issue(t0 + col_of(f2), rb);     // flies while ra is processed
-                    process(ra, f);
-                    if (f2 >= n_pairs) break;
+                    int mt2 = mt, u2 = u;
+                    advance(mt2, u2);
+                    if (mt2 < mt_count) tmem_ld16_issue(t0 + (uint32_t)(mt2 * CC + u2 * 16), rb);     // flies while ra is processed
+                    process(ra, mt, u);
+                    if (mt2 >= mt_count) break;
                     tmem_ld16_wait(rb);
-                    const int f3 = f2 + NG;
-                    if (f3 < n_pairs) tmem_ld16_issue(t0 + col_of(f3), ra);
-                    process(rb, f2);
-                    f = f3;
+                    mt = mt2; u = u2;
+                    advance(mt, u);
+                    if (mt < mt_count) tmem_ld16_issue(t0 + (uint32_t)(mt * CC + u * 16), ra);
+                    process(rb, mt2, u2);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            k1w::arrive(&bar_t_empty[buf]);
-            k1w::arrive(&bar_e_full[buf]);
+            k1w::arrive(b_t_empty + 8 * buf);
+            k1w::arrive(b_e_full + 8 * buf);
         }
     } else if (warp >= 4 + p.n_epi) {
         // =========================================================================== depthwise on E
@@ -337,13 +364,14 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
         const uint32_t cst = sC + (uint32_t)CC * 4 + (uint32_t)cv * 16;         // this thread's column of the constants
         const int c0 = cbase + cv * 4;
         T* const out = reinterpret_cast<T*>(p.out);
-        int k = 0;
-        for (int item = group; item < p.items; item += p.groups, ++k) {
-            const Geo g = geom(item);
+        const long long crop_elems = (long long)p.Ho * p.Ho * p.Cexp;
+        for (int k = 0; it.item < p.items; it.next(), ++k) {
+            const int tyi = div_small(it.t, inv_tx);
+            const int ty0 = tyi * p.TH, tx0 = (it.t - tyi * p.tiles_x) * p.TW, n0 = it.q * p.NB;
             const int buf = k & 1;
-            const bool dw_active = lane_ok && g.n0 + jc < p.N;
-            T* const out_n = out + (long long)(g.n0 + jc) * p.Ho * p.Ho * p.Cexp;
-            k1w::wait(&bar_e_full[buf], (k >> 1) & 1, s_abort, p.tflag);
+            const bool dw_active = lane_ok && n0 + jc < p.N;
+            T* const out_n = out + (long long)(n0 + jc) * crop_elems;
+            k1w::wait_t(b_e_full + 8 * buf, (k >> 1) & 1, s_abort, p.tflag, tr, tw0);
             float sum[4] = {0.f, 0.f, 0.f, 0.f};
             if (dw_active) {
                 const float4 bq = lds_f4(cst);
@@ -382,8 +410,7 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
                         }
                         erow += e_rowstride;
                     }
-                    const int oy = g.ty0 + oyl;
-                    T* dst = out_n + ((long long)oy * p.Ho + g.tx0 + oxl0) * p.Cexp + c0;
+                    T* dst = out_n + ((long long)(ty0 + oyl) * p.Ho + tx0 + oxl0) * p.Cexp + c0;
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         if (oxl0 + r < p.TW) {
@@ -397,16 +424,18 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
                     }
                 }
             }
-            k1w::arrive(&bar_e_empty[buf]);                   // every depthwise thread: its reads of this E are done
+            k1w::arrive(b_e_empty + 8 * buf);                 // every depthwise thread: its reads of this E are done
             // squeeze partial sums of the item: lanes -> shared memory -> one fixed-order column sum per (crop, channel)
             const uint32_t r_buf = sR + (uint32_t)(buf * p.PY * CC) * 4;
             if (lane_ok)
                 asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(r_buf + (uint32_t)(py * CC + cv * 4) * 4),
                              "f"(sum[0]), "f"(sum[1]), "f"(sum[2]), "f"(sum[3]) : "memory");
+            const long long tb0 = tr ? clock64() : 0;
             asm volatile("bar.sync 1, %0;" ::"r"(p.n_dw) : "memory");
+            if (tr) tw1 += clock64() - tb0;
             if (dtid < p.NB * CC) {
                 const int jj = dtid >= CC ? 1 : 0, cc = dtid - jj * CC;          // NB <= 2
-                if (g.n0 + jj < p.N) {
+                if (n0 + jj < p.N) {
                     float s4[4] = {0.f, 0.f, 0.f, 0.f};
                     const uint32_t r0 = r_buf + (uint32_t)(jj * p.PYc * CC + cc) * 4;
                     int y = 0;
@@ -423,11 +452,18 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
                         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(r0 + (uint32_t)(y * CC) * 4));
                         s4[y & 3] += t;
                     }
-                    p.partial[((long long)(g.n0 + jj) * p.tiles + g.tile) * p.Cexp + cbase + cc] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                    p.partial[((long long)(n0 + jj) * p.tiles + it.t) * p.Cexp + cbase + cc] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
                 }
             }
             // the squeeze scratch of this parity is rewritten two items later, after the next named barrier
         }
+    }
+    if (tr && (warp == 0 || warp == 1 || warp == 4 || warp == 4 + p.n_epi)) {
+        // trace row of this CTA: [0] total cycles, then per role (producer, MMA, epilogue warp 0, depthwise warp 0): its waits
+        long long* row = p.trace + (long long)blockIdx.x * 16;
+        const int slot = warp == 0 ? 1 : (warp == 1 ? 4 : (warp == 4 ? 7 : 10));
+        row[slot] = tw0; row[slot + 1] = tw1; row[slot + 2] = clock64() - t_begin;
+        if (warp == 0) row[0] = clock64() - t_begin;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

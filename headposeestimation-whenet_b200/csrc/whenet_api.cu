@@ -153,6 +153,8 @@ struct whenet_ctx {
     std::vector<CUtensorMap> tmap_w;        // weight tensor maps of K1W by block
     std::vector<K1PPlan> k1p;  // k1_variant 3: persistent warp-specialised K1 for the blocks with several tiles per crop
     int sm_count = 148;
+    int k1w_trace_block = 0;   // debug: the K1W launch of this block records where its roles wait (whenet_debug_read_trace)
+    long long* d_trace = nullptr;
     int k1p_epi_warps = 8;     // epilogue group of K1P: 4 or 8 warps (the depthwise group gets the other 10 or 6)
     int k1p_min_crops = 8;     // below this a persistent grid cannot fill the SMs: K1 with its chunk split is used instead
     K1Plan dw1;                // block 1 (no expand): depthwise-only instance of K1
@@ -493,6 +495,12 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
                 }
                 p.tmA = it->second; p.tmW = c->tmap_w[i];
                 p.shift = w.b_exp_h; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial; p.tflag = c->d_tflag;
+                p.trace = nullptr;
+                if (c->k1w_trace_block == b.idx) {
+                    if (!c->d_trace) CK(cudaMalloc(&c->d_trace, 256 * 16 * sizeof(long long)));
+                    CK(cudaMemsetAsync(c->d_trace, 0, 256 * 16 * sizeof(long long), c->stream));
+                    p.trace = c->d_trace;
+                }
                 snprintf(nm, sizeof nm, "b%02d.k1", b.idx);
                 Scope sc(c, nm, (double)nb * ((double)b.hin * b.hin * b.cin + (double)b.hout * b.hout * b.cexp) * sizeof(T),
                          2.0 * nb * ((double)b.hin * b.hin * b.cin * b.cexp + (double)b.hout * b.hout * b.k * b.k * b.cexp));
@@ -1300,6 +1308,15 @@ int whenet_debug_decode(whenet_ctx* c, const float* logits_host, int n, float* a
     return 0;
 }
 
+int whenet_debug_read_trace(whenet_ctx* c, int64_t* out, int n_rows) {
+    if (!c || !out || n_rows < 1 || n_rows > 256) return fail(WHENET_EINVAL, "bad arguments");
+    if (!c->d_trace) return fail(WHENET_ENOTFOUND, "no trace recorded (set option k1w_trace to a block index and run a forward)");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out, c->d_trace, (size_t)n_rows * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int whenet_debug_raise_timeout(whenet_ctx* c) {
     if (!c) return fail(WHENET_EINVAL, "null context");
     CK(cudaSetDevice(c->device));
@@ -1323,6 +1340,27 @@ int whenet_debug_set_k1_plan(whenet_ctx* c, int block, int th, int tw, int r, in
     pl.R = r;
     pl.NT = nt;
     c->k1[block - 1] = pl;
+    c->cfg_epoch++;
+    free_ws(c);      // the squeeze-partials buffer depends on the tile count
+    return 0;
+}
+
+int whenet_debug_set_k1w_plan(whenet_ctx* c, int block, int th, int tw, int r, int cc, int nb, int n_epi, int nt) {
+    if (!c || block < 2 || block > (int)c->blocks.size()) return fail(WHENET_EINVAL, "bad block index");
+    if (c->precision == WHENET_PRECISION_FP32) return fail(WHENET_EINVAL, "K1W needs a 16-bit storage mode");
+    const BlockCfg& b = c->blocks[block - 1];
+    if (!whenet::fused::k1w_has_instance(b.k, b.s, r, nt)) return fail(WHENET_EINVAL, "no K1W instantiation for k=%d s=%d r=%d nt=%d", b.k, b.s, r, nt);
+    K1WPlan pw;
+    pw.valid = whenet::fused::plan_k1w_candidate(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, c->precision == WHENET_PRECISION_BF16, th, tw, r, cc, nb,
+                                                 n_epi, nt, &pw.p, &pw.smem);
+    if (!pw.valid) return fail(WHENET_EINVAL, "K1W plan %dx%d r%d cc%d nb%d epi%d nt%d does not fit block %d", th, tw, r, cc, nb, n_epi, nt, block);
+    pw.R = r; pw.NT = nt;
+    if (c->weights_loaded) {
+        int rc = make_tmap_w(&c->tmap_w[block - 1], c->bw[block - 1].wt_exp_h, b.cexp, b.cin, cc, c->precision == WHENET_PRECISION_BF16);
+        if (rc) return rc;
+    }
+    c->k1w[block - 1] = pw;
+    c->tmaps.clear();
     c->cfg_epoch++;
     free_ws(c);      // the squeeze-partials buffer depends on the tile count
     return 0;
@@ -1388,6 +1426,7 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!strcmp(key, "se_scale_out")) { c->se_scale_out = value; return 0; }
     if (!strcmp(key, "k1_split_ctas")) { c->k1_split_ctas = value; return 0; }
     if (!strcmp(key, "k1p_min_crops")) { c->k1p_min_crops = value; return 0; }
+    if (!strcmp(key, "k1w_trace")) { c->k1w_trace_block = value; return 0; }
     if (!strcmp(key, "k1p_epi_warps")) {
         if (value != 4 && value != 8) return fail(WHENET_EINVAL, "k1p_epi_warps is 4 or 8");
         c->k1p_epi_warps = value;
@@ -1441,6 +1480,7 @@ void whenet_destroy(whenet_ctx* c) {
     if (c->d_angles) cudaFree(c->d_angles);
     if (c->d_logits) cudaFree(c->d_logits);
     if (c->h_tflag) cudaFreeHost(c->h_tflag);
+    if (c->d_trace) cudaFree(c->d_trace);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_ready[i]) cudaEventDestroy(c->ev_ready[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);

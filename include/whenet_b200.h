@@ -156,6 +156,16 @@ int whenet_debug_decode(whenet_ctx* ctx, const float* logits_host, int n, float*
  * the next synchronising call (host-output forward, whenet_synchronize) must return WHENET_ECUDA. */
 int whenet_debug_raise_timeout(whenet_ctx* ctx);
 
+/* Where the warp roles of the K1W kernel waited: set option "k1w_trace" to a block index (2..16), run a forward, then read
+ * n_rows x 16 int64 cycle counters (one row per CTA): [0] CTA cycles; producer [1] wait a_empty [3] busy span; MMA [4] wait
+ * a_full [5] wait t_empty; epilogue warp 0 [7] wait t_full [8] wait e_empty [9] span; depthwise warp 0 [10] wait e_full
+ * [11] group barrier [12] span. */
+int whenet_debug_read_trace(whenet_ctx* ctx, int64_t* out, int n_rows);
+
+/* Same for K1W (option "k1_variant" = 4, every block with an expand conv): output tile, strip length, channels per CTA,
+ * crops per item (2 only where one tile is the whole image), epilogue warps (4 or 8), threads per CTA (640 or 768). */
+int whenet_debug_set_k1w_plan(whenet_ctx* ctx, int block, int th, int tw, int r, int cc, int nb, int n_epi, int nt);
+
 /* Same for K1P (option "k1_variant" = 3; blocks with several tiles per crop): tile, strip and chunk shape plus the
  * size of the TMEM-epilogue warp group (4 or 8; the depthwise group gets the remaining warps of the 512-thread CTA). */
 int whenet_debug_set_k1p_plan(whenet_ctx* ctx, int block, int th, int tw, int r, int cc, int epi_warps);
