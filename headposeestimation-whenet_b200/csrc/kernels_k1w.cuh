@@ -18,8 +18,11 @@
 //   * warp roles, connected by mbarriers (no CTA-wide barrier in the item loop):
 //       warp 0            TMA producer   A ring (NA stages)
 //       warp 1            MMA issuer     tcgen05.mma into a 2-deep TMEM accumulator ring, tcgen05.commit -> mbarrier
+//       warps 2-3         reducer        fixed-order column sums of the depthwise lanes' squeeze partials -> global
 //       warps 4..4+E-1    epilogue       TMEM -> +shift -> swish -> 16-bit -> E ring (2 deep); rows outside the image -> 0
-//       remaining warps   depthwise      E -> k x k FFMA2 -> +shift, swish -> D, squeeze sums (named barrier in the group)
+//       remaining warps   depthwise      E -> k x k FFMA2 -> +shift, swish -> D; per-lane squeeze sums -> smem ring
+//     Registers follow the roles (setmaxnreg): 48 for the control group, 72-80 for the epilogue, 88-96 for the depthwise
+//     warps, which lets 12-16 of them run beside 4-8 epilogue warps in one 768-thread CTA.
 //     so the SFU-bound epilogue of item i+1, the FMA-bound depthwise of item i, the tensor core and the TMA unit all run
 //     at the same time.
 //
@@ -153,11 +156,13 @@ struct ItemIter {
     }
 };
 
-template <typename T, int KS, int S, int R, int NT>
-__global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WParams p) {
+constexpr int kK1WThreads = 768;       // six warpgroups: control | EPI_WG x epilogue | (5 - EPI_WG) x depthwise
+
+template <typename T, int KS, int S, int R, int EPI_WG>
+__global__ void __maxnreg__(80) k1w_kernel(const __grid_constant__ K1WParams p) {
     extern __shared__ uint8_t smem_raw[];
-    // [0,1] a_full  [2,3] a_empty  [4,5] t_full  [6,7] t_empty  [8,9] e_full  [10,11] e_empty  [12] w
-    __shared__ __align__(8) uint64_t bars[13];
+    // [0,1] a_full  [2,3] a_empty  [4,5] t_full  [6,7] t_empty  [8,9] e_full  [10,11] e_empty  [12] w  [13,14] r_full  [15,16] r_empty
+    __shared__ __align__(8) uint64_t bars[17];
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_abort_mem;
     volatile int* s_abort = &s_abort_mem;
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
     const uint32_t sA = smem0, sW = smem0 + p.off_w, sC = smem0 + p.off_c, sE = smem0 + p.off_e, sR = smem0 + p.off_r;
     const uint32_t bar0 = tc::smem_u32(&bars[0]);
     const uint32_t b_a_full = bar0, b_a_empty = bar0 + 16, b_t_full = bar0 + 32, b_t_empty = bar0 + 48, b_e_full = bar0 + 64,
-                   b_e_empty = bar0 + 80, b_w = bar0 + 96;
+                   b_e_empty = bar0 + 80, b_w = bar0 + 96, b_r_full = bar0 + 104, b_r_empty = bar0 + 120;
     const int CC = p.CC, pitchE = p.pitchE;
     const int chunk = blockIdx.x % p.n_chunks, group = blockIdx.x / p.n_chunks;
     const int cbase = chunk * CC;
@@ -184,6 +189,8 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
             tc::mbar_init(&bars[6 + i], n_epi_threads);
             tc::mbar_init(&bars[8 + i], n_epi_threads);
             tc::mbar_init(&bars[10 + i], p.n_dw);
+            tc::mbar_init(&bars[13 + i], p.n_dw);
+            tc::mbar_init(&bars[15 + i], 64);
         }
         tc::mbar_init(&bars[12], 1);
         s_abort_mem = 0;
@@ -198,11 +205,17 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem_base;
 
+    // registers follow the roles: the launch gives every thread 80; control and epilogue groups hand theirs back, the
+    // depthwise groups (the only code with 28-56 accumulators + a kernel row of weights live) take them
+    // (each setmaxnreg sits at the top of its role's branch: ptxas budgets the code it dominates)
+
     const float inv_tx = 1.0f / (float)p.tiles_x;
     ItemIter it;
     it.init(group, p.groups, p.tiles);
 
-    if (warp == 0) {
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+      if (warp == 0) {
         // =========================================================================== TMA producer
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA) : "memory");
@@ -221,7 +234,7 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
                     k1w::tma_4d(sA + (uint32_t)st * p.a_stage + (uint32_t)kb * p.rows_alloc * 128, &p.tmA, kb * 64, ix0, iy0, it.q * p.NB, b_a_full + 8 * st);
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         // =========================================================================== MMA issuer
         k1w::wait(b_w, 0, s_abort, p.tflag);
         for (int k = 0; it.item < p.items; it.next(), ++k) {
@@ -246,7 +259,44 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
             }
             __syncwarp();
         }
-    } else if (warp >= 4 && warp < 4 + p.n_epi) {
+      } else {
+        // =========================================================================== reducer: squeeze partial sums of an item
+        // The depthwise lanes leave their per-lane sums in a 2-slot ring; these two warps add them up in a FIXED order
+        // (four chains by lane mod 4, as K1 does) and write partial[crop][tile][channel].  The depthwise warps never wait
+        // for each other, so they drift apart and their SFU / FMA phases interleave.
+        const int rtid = tid - 64;
+        for (int k = 0; it.item < p.items; it.next(), ++k) {
+            const int buf = k & 1, n0 = it.q * p.NB;
+            k1w::wait(b_r_full + 8 * buf, (k >> 1) & 1, s_abort, p.tflag);
+            const uint32_t r_buf = sR + (uint32_t)(buf * p.PY * CC) * 4;
+            for (int col = rtid; col < p.NB * CC; col += 64) {
+                const int jj = col >= CC ? 1 : 0, cc = col - jj * CC;          // NB <= 2
+                float s4[4] = {0.f, 0.f, 0.f, 0.f};
+                const uint32_t r0 = r_buf + (uint32_t)(jj * p.PYc * CC + cc) * 4;
+                int y = 0;
+                for (; y + 3 < p.PYc; y += 4) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float t;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(r0 + (uint32_t)((y + i) * CC) * 4));
+                        s4[i] += t;
+                    }
+                }
+                for (; y < p.PYc; ++y) {
+                    float t;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(r0 + (uint32_t)(y * CC) * 4));
+                    s4[y & 3] += t;
+                }
+                if (n0 + jj < p.N)
+                    p.partial[((long long)(n0 + jj) * p.tiles + it.t) * p.Cexp + cbase + cc] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            }
+            k1w::arrive(b_r_empty + 8 * buf);
+        }
+      }
+    } else if (warp < 4 + 4 * EPI_WG) {
+        // register budget of the CTA: 768 x 80 = 61440 = 128 x 48 (control) + 128 x 80 + 512 x 88   (one epilogue group)
+        //                                               = 128 x 48 (control) + 256 x 72 + 384 x 96   (two epilogue groups)
+        if (EPI_WG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");          // one group: keeps its 80
         // =========================================================================== epilogue: TMEM -> +shift -> swish -> E
         const int q4 = warp & 3;                       // TMEM lane quadrant of this warp
         const int grp = (warp - 4) >> 2, NG = p.n_epi >> 2;
@@ -342,7 +392,9 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
             k1w::arrive(b_t_empty + 8 * buf);
             k1w::arrive(b_e_full + 8 * buf);
         }
-    } else if (warp >= 4 + p.n_epi) {
+    } else {
+        if (EPI_WG == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
         // =========================================================================== depthwise on E
         const int dtid = tid - (k1w::kCtrlThreads + n_epi_threads);
         const int CVc = CC >> 2;
@@ -372,7 +424,7 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
             const bool dw_active = lane_ok && n0 + jc < p.N;
             T* const out_n = out + (long long)(n0 + jc) * crop_elems;
             k1w::wait_t(b_e_full + 8 * buf, (k >> 1) & 1, s_abort, p.tflag, tr, tw0);
-            float sum[4] = {0.f, 0.f, 0.f, 0.f};
+            float2 sum01 = make_float2(0.f, 0.f), sum23 = make_float2(0.f, 0.f);
             if (dw_active) {
                 const float4 bq = lds_f4(cst);
                 const uint32_t e_cv = sE + (uint32_t)buf * p.e_buf + (uint32_t)(jc * p.e_rows) * pitchE + (uint32_t)cv * 8;
@@ -415,7 +467,7 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
                     for (int r = 0; r < R; ++r) {
                         if (oxl0 + r < p.TW) {
                             const float2 s01 = k1w::swish2_from_half(acc[r][0]), s23 = k1w::swish2_from_half(acc[r][1]);
-                            sum[0] += s01.x; sum[1] += s01.y; sum[2] += s23.x; sum[3] += s23.y;
+                            sum01 = k1w::fadd2(sum01, s01); sum23 = k1w::fadd2(sum23, s23);
                             uint2 o;
                             o.x = pack2<T>(s01.x, s01.y);
                             o.y = pack2<T>(s23.x, s23.y);
@@ -425,40 +477,15 @@ __global__ void __launch_bounds__(NT, 1) k1w_kernel(const __grid_constant__ K1WP
                 }
             }
             k1w::arrive(b_e_empty + 8 * buf);                 // every depthwise thread: its reads of this E are done
-            // squeeze partial sums of the item: lanes -> shared memory -> one fixed-order column sum per (crop, channel)
-            const uint32_t r_buf = sR + (uint32_t)(buf * p.PY * CC) * 4;
+            // squeeze partial sums of the item: this lane's sums -> ring slot; the reducer warps take it from there
+            k1w::wait_t(b_r_empty + 8 * buf, ((k >> 1) & 1) ^ 1, s_abort, p.tflag, tr, tw1);
             if (lane_ok)
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(r_buf + (uint32_t)(py * CC + cv * 4) * 4),
-                             "f"(sum[0]), "f"(sum[1]), "f"(sum[2]), "f"(sum[3]) : "memory");
-            const long long tb0 = tr ? clock64() : 0;
-            asm volatile("bar.sync 1, %0;" ::"r"(p.n_dw) : "memory");
-            if (tr) tw1 += clock64() - tb0;
-            if (dtid < p.NB * CC) {
-                const int jj = dtid >= CC ? 1 : 0, cc = dtid - jj * CC;          // NB <= 2
-                if (n0 + jj < p.N) {
-                    float s4[4] = {0.f, 0.f, 0.f, 0.f};
-                    const uint32_t r0 = r_buf + (uint32_t)(jj * p.PYc * CC + cc) * 4;
-                    int y = 0;
-                    for (; y + 3 < p.PYc; y += 4) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float t;
-                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(r0 + (uint32_t)((y + i) * CC) * 4));
-                            s4[i] += t;
-                        }
-                    }
-                    for (; y < p.PYc; ++y) {
-                        float t;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(r0 + (uint32_t)(y * CC) * 4));
-                        s4[y & 3] += t;
-                    }
-                    p.partial[((long long)(n0 + jj) * p.tiles + it.t) * p.Cexp + cbase + cc] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-                }
-            }
-            // the squeeze scratch of this parity is rewritten two items later, after the next named barrier
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sR + (uint32_t)((buf * p.PY + py) * CC + cv * 4) * 4),
+                             "f"(sum01.x), "f"(sum01.y), "f"(sum23.x), "f"(sum23.y) : "memory");
+            k1w::arrive(b_r_full + 8 * buf);
         }
     }
-    if (tr && (warp == 0 || warp == 1 || warp == 4 || warp == 4 + p.n_epi)) {
+    if (tr && (warp == 0 || warp == 1 || warp == 4 || warp == 4 + 4 * EPI_WG)) {
         // trace row of this CTA: [0] total cycles, then per role (producer, MMA, epilogue warp 0, depthwise warp 0): its waits
         long long* row = p.trace + (long long)blockIdx.x * 16;
         const int slot = warp == 0 ? 1 : (warp == 1 ? 4 : (warp == 4 ? 7 : 10));
@@ -500,6 +527,7 @@ inline bool plan_k1w_candidate(int Hin, int Ho, int Cin, int Cexp, int k, int s,
     p->pitchE = CC * 2 + 16;
     p->e_rows = p->IH * p->IW + R * s + 16;          // a ragged strip still LOADS the columns of its discarded outputs
     p->n_epi = n_epi;
+    if (NT != kK1WThreads) return false;
     p->n_dw = NT - k1w::kCtrlThreads - 32 * n_epi;
     if (p->n_dw < 64 || (p->n_dw & 31)) return false;
     const int CVc = CC / 4;
@@ -537,16 +565,16 @@ inline bool plan_k1w(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, 
     struct Tuned { int hin, k, s, cexp; K1WChoice c; };
     static const Tuned tuned[] = {
         {112, 3, 2, 96, {8, 8, 4, 48, 1, 8, 768}},      // block 2: 17x17 halo = 289 rows, SFU-bound -> 8 epilogue warps
-        {56, 3, 1, 144, {14, 14, 7, 48, 1, 4, 640}},    // block 3: 16x16 = 256 rows
+        {56, 3, 1, 144, {14, 14, 7, 48, 1, 4, 768}},    // block 3: 16x16 = 256 rows
         {56, 5, 2, 144, {7, 7, 4, 48, 1, 8, 768}},      // block 4: 17x17
-        {28, 5, 1, 240, {14, 14, 7, 48, 1, 4, 640}},    // block 5: 18x18 = 324 rows
-        {28, 3, 2, 240, {7, 7, 4, 48, 1, 8, 768}},      // block 6: 15x15 = 225 rows
-        {14, 3, 1, 480, {14, 14, 7, 48, 1, 4, 640}},    // blocks 7, 8: whole image, 16x16
-        {14, 5, 1, 480, {14, 14, 7, 48, 1, 4, 640}},    // block 9: 18x18
-        {14, 5, 1, 672, {14, 14, 7, 48, 1, 4, 640}},    // blocks 10, 11
-        {14, 5, 2, 672, {7, 7, 4, 48, 1, 8, 768}},      // block 12: 17x17
-        {7, 5, 1, 1152, {7, 7, 4, 48, 2, 4, 640}},      // blocks 13-15: two crops per item, 2 x 11x11 = 242 rows
-        {7, 3, 1, 1152, {7, 7, 4, 48, 2, 4, 640}},      // block 16: 2 x 9x9 = 162 rows
+        {28, 5, 1, 240, {14, 14, 7, 80, 1, 4, 768}},    // block 5: 18x18 = 324 rows
+        {28, 3, 2, 240, {7, 7, 4, 80, 1, 8, 768}},      // block 6: 15x15 = 225 rows
+        {14, 3, 1, 480, {14, 14, 7, 96, 1, 4, 768}},    // blocks 7, 8: whole image, 16x16
+        {14, 5, 1, 480, {14, 14, 7, 48, 1, 4, 768}},    // block 9: 18x18
+        {14, 5, 1, 672, {14, 14, 7, 48, 1, 4, 768}},    // blocks 10, 11
+        {14, 5, 2, 672, {7, 7, 4, 48, 1, 4, 768}},      // block 12: 17x17
+        {7, 5, 1, 1152, {7, 7, 4, 64, 2, 4, 768}},      // blocks 13-15: two crops per item, 2 x 11x11 = 242 rows
+        {7, 3, 1, 1152, {7, 7, 7, 96, 2, 4, 768}},      // block 16: 2 x 9x9 = 162 rows
     };
     for (const Tuned& t : tuned)
         if (t.hin == Hin && t.k == k && t.s == s && t.cexp == Cexp) {
@@ -561,7 +589,7 @@ inline bool plan_k1w(int Hin, int Ho, int Cin, int Cexp, int k, int s, int pad, 
 }
 
 inline bool k1w_has_instance(int k, int s, int R, int NT) {
-    return (k == 3 || k == 5) && (s == 1 || s == 2) && (R == 4 || R == 7) && (NT == 640 || NT == 768);
+    return (k == 3 || k == 5) && (s == 1 || s == 2) && (R == 4 || R == 7) && NT == kK1WThreads;
 }
 
 template <typename T>
@@ -574,17 +602,18 @@ int launch_k1w(cudaStream_t stream, K1WParams p, int k, int s, int R, int NT, si
     p.groups = groups;
     const int ctas = groups * p.n_chunks;
     if (ctas < 1) return 0;
-#define K1W_GO(KS, S, RR, NTT)                                                                                             \
+#define K1W_GO(KS, S, RR, EW)                                                                                              \
     do {                                                                                                                   \
-        auto kfn = k1w_kernel<T, KS, S, RR, NTT>;                                                                          \
+        auto kfn = k1w_kernel<T, KS, S, RR, EW>;                                                                           \
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_MAX_SMEM) != cudaSuccess) return -1;  \
-        kfn<<<ctas, NTT, smem, stream>>>(p);                                                                               \
+        kfn<<<ctas, kK1WThreads, smem, stream>>>(p);                                                                       \
         return 0;                                                                                                          \
     } while (0)
 #define K1W(KS, S, RR)                                  \
     do {                                                \
-        if (NT == 640) K1W_GO(KS, S, RR, 640);          \
-        if (NT == 768) K1W_GO(KS, S, RR, 768);          \
+        if (NT != kK1WThreads) return 1;                \
+        if (p.n_epi == 4) K1W_GO(KS, S, RR, 1);         \
+        if (p.n_epi == 8) K1W_GO(KS, S, RR, 2);         \
     } while (0)
     if (k == 3 && s == 2 && R == 4) K1W(3, 2, 4);
     if (k == 3 && s == 1 && R == 7) K1W(3, 1, 7);

@@ -296,7 +296,7 @@ class WHENet:
         """Tuning hook (see whenet_debug_set_k1_plan); returns False when the plan cannot run."""
         return self._L.whenet_debug_set_k1_plan(self._h, block, th, tw, r, cc, nt, nb) == 0
 
-    def set_k1w_plan(self, block: int, th: int, tw: int, r: int, cc: int, nb: int = 1, n_epi: int = 4, nt: int = 640) -> bool:
+    def set_k1w_plan(self, block: int, th: int, tw: int, r: int, cc: int, nb: int = 1, n_epi: int = 4, nt: int = 768) -> bool:
         """Tuning hook for the weight-stationary variant (see whenet_debug_set_k1w_plan); False when the plan cannot run."""
         return self._L.whenet_debug_set_k1w_plan(self._h, block, th, tw, r, cc, nb, n_epi, nt) == 0
 

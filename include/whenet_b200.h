@@ -163,7 +163,7 @@ int whenet_debug_raise_timeout(whenet_ctx* ctx);
 int whenet_debug_read_trace(whenet_ctx* ctx, int64_t* out, int n_rows);
 
 /* Same for K1W (option "k1_variant" = 4, every block with an expand conv): output tile, strip length, channels per CTA,
- * crops per item (2 only where one tile is the whole image), epilogue warps (4 or 8), threads per CTA (640 or 768). */
+ * crops per item (2 only where one tile is the whole image), epilogue warps (4 or 8), threads per CTA (768). */
 int whenet_debug_set_k1w_plan(whenet_ctx* ctx, int block, int th, int tw, int r, int cc, int nb, int n_epi, int nt);
 
 /* Same for K1P (option "k1_variant" = 3; blocks with several tiles per crop): tile, strip and chunk shape plus the

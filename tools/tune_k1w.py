@@ -17,17 +17,17 @@ def t_block(blk):
     return {s["name"]: s["ms"] / s["launches"] for s in st}["b%02d.k1" % blk]
 # (th, tw, r, cc, nb, n_epi, nt)
 CANDS = {
-    2: [(8, 8, 4, 48, 1, 8, 768), (8, 8, 4, 48, 1, 4, 640), (8, 8, 4, 32, 1, 8, 768), (8, 4, 4, 96, 1, 8, 768), (8, 8, 4, 48, 1, 4, 768)],
-    3: [(14, 14, 7, 48, 1, 4, 640), (14, 14, 7, 48, 1, 8, 768), (14, 14, 7, 48, 1, 4, 768), (7, 14, 7, 144, 1, 4, 640), (14, 14, 4, 48, 1, 4, 640)],
-    4: [(7, 7, 4, 48, 1, 8, 768), (7, 7, 4, 48, 1, 4, 640), (7, 7, 7, 48, 1, 8, 768), (7, 7, 4, 48, 1, 4, 768)],
-    5: [(14, 14, 7, 48, 1, 4, 640), (14, 14, 7, 80, 1, 4, 640), (14, 14, 4, 80, 1, 4, 640), (14, 14, 7, 48, 1, 4, 768), (14, 14, 7, 80, 1, 8, 768)],
-    6: [(7, 7, 4, 48, 1, 8, 768), (7, 7, 4, 80, 1, 8, 768), (7, 7, 7, 80, 1, 4, 640), (7, 7, 4, 80, 1, 4, 640), (14, 14, 7, 48, 1, 4, 640)],
-    7: [(14, 14, 7, 48, 1, 4, 640), (14, 14, 7, 80, 1, 4, 640), (14, 14, 7, 96, 1, 4, 640), (14, 14, 7, 96, 1, 8, 768), (14, 14, 4, 96, 1, 4, 640)],
-    9: [(14, 14, 7, 48, 1, 4, 640), (14, 14, 7, 80, 1, 4, 640), (14, 14, 4, 80, 1, 4, 640), (14, 14, 7, 80, 1, 4, 768)],
-    10: [(14, 14, 7, 48, 1, 4, 640), (14, 14, 4, 48, 1, 4, 640), (14, 14, 7, 32, 1, 4, 640), (14, 14, 7, 48, 1, 4, 768)],
-    12: [(7, 7, 4, 48, 1, 8, 768), (7, 7, 4, 48, 1, 4, 640), (7, 7, 7, 48, 1, 4, 640), (7, 7, 4, 96, 1, 4, 640), (7, 7, 4, 32, 1, 4, 640)],
-    13: [(7, 7, 4, 48, 2, 4, 640), (7, 7, 4, 64, 2, 4, 640), (7, 7, 7, 64, 2, 4, 640), (7, 7, 4, 64, 1, 4, 640), (7, 7, 4, 128, 1, 4, 640), (7, 7, 4, 96, 1, 4, 640)],
-    16: [(7, 7, 4, 48, 2, 4, 640), (7, 7, 4, 64, 2, 4, 640), (7, 7, 7, 96, 2, 4, 640), (7, 7, 4, 128, 2, 4, 640), (7, 7, 4, 128, 1, 4, 640), (7, 7, 7, 192, 1, 4, 640)],
+    2: [(8, 8, 4, 48, 1, 8, 768), (8, 8, 4, 48, 1, 4, 768), (8, 4, 4, 96, 1, 8, 768), (8, 8, 4, 32, 1, 8, 768)],
+    3: [(14, 14, 7, 48, 1, 4, 768), (14, 14, 7, 48, 1, 8, 768), (14, 14, 4, 48, 1, 4, 768)],
+    4: [(7, 7, 4, 48, 1, 8, 768), (7, 7, 4, 48, 1, 4, 768), (7, 7, 7, 48, 1, 8, 768)],
+    5: [(14, 14, 7, 80, 1, 4, 768), (14, 14, 7, 48, 1, 4, 768), (14, 14, 7, 80, 1, 8, 768), (14, 14, 4, 80, 1, 4, 768)],
+    6: [(7, 7, 4, 80, 1, 8, 768), (7, 7, 4, 80, 1, 4, 768), (7, 7, 7, 80, 1, 4, 768), (7, 7, 4, 48, 1, 8, 768)],
+    7: [(14, 14, 7, 96, 1, 4, 768), (14, 14, 7, 96, 1, 8, 768), (14, 14, 7, 160, 1, 4, 768), (14, 14, 4, 96, 1, 4, 768)],
+    9: [(14, 14, 7, 48, 1, 4, 768), (14, 14, 7, 48, 1, 8, 768), (14, 14, 4, 48, 1, 4, 768), (14, 14, 7, 32, 1, 4, 768)],
+    10: [(14, 14, 7, 48, 1, 4, 768), (14, 14, 7, 48, 1, 8, 768), (14, 14, 4, 48, 1, 4, 768)],
+    12: [(7, 7, 4, 48, 1, 4, 768), (7, 7, 4, 48, 1, 8, 768), (7, 7, 7, 48, 1, 4, 768)],
+    13: [(7, 7, 4, 64, 2, 4, 768), (7, 7, 7, 64, 2, 4, 768), (7, 7, 4, 128, 1, 4, 768), (7, 7, 4, 48, 2, 4, 768)],
+    16: [(7, 7, 7, 96, 2, 4, 768), (7, 7, 7, 192, 1, 4, 768), (7, 7, 4, 64, 2, 4, 768), (7, 7, 4, 128, 1, 4, 768)],
 }
 for blk in [int(b) for b in os.environ.get("BLOCKS", "2,3,4,5,6,7,9,10,12,13,16").split(",")]:
     base = None
