@@ -293,20 +293,21 @@ __global__ void __maxnreg__(80) k1w_kernel(const __grid_constant__ K1WParams p) 
             k1w::arrive(b_r_empty + 8 * buf);
         }
       }
-    } else if (warp < 4 + 4 * EPI_WG) {
+    } else if (warp >= 24 - 4 * EPI_WG) {
         // register budget of the CTA: 768 x 80 = 61440 = 128 x 48 (control) + 128 x 80 + 512 x 88   (one epilogue group)
         //                                               = 128 x 48 (control) + 256 x 72 + 384 x 96   (two epilogue groups)
         if (EPI_WG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");          // one group: keeps its 80
         // =========================================================================== epilogue: TMEM -> +shift -> swish -> E
         const int q4 = warp & 3;                       // TMEM lane quadrant of this warp
-        const int grp = (warp - 4) >> 2, NG = p.n_epi >> 2;
+        const int e_first = kK1WThreads - n_epi_threads;     // first epilogue thread
+        const int grp = (warp - (e_first >> 5)) >> 2, NG = p.n_epi >> 2;
         const int units = CC >> 4;
         const int npix = p.IH * p.IW;
         const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
         // BN shifts of this CTA's channels -> shared memory (read by this group only; published by a group barrier)
         {
             float* sh = reinterpret_cast<float*>(smem_raw + (sC - tc::smem_u32(smem_raw)));
-            for (int c = tid - k1w::kCtrlThreads; c < CC; c += n_epi_threads) sh[c] = p.shift[cbase + c];
+            for (int c = tid - e_first; c < CC; c += n_epi_threads) sh[c] = p.shift[cbase + c];
             asm volatile("bar.sync 2, %0;" ::"r"(n_epi_threads) : "memory");
         }
         // rows of this thread: r = mt * 128 + q4 * 32 + lane.  Their crop / position inside the halo tile and their E row
@@ -396,7 +397,7 @@ __global__ void __maxnreg__(80) k1w_kernel(const __grid_constant__ K1WParams p) 
         if (EPI_WG == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
         // =========================================================================== depthwise on E
-        const int dtid = tid - (k1w::kCtrlThreads + n_epi_threads);
+        const int dtid = tid - k1w::kCtrlThreads;
         const int CVc = CC >> 2;
         const int py = div_small(dtid, 1.0f / (float)CVc), cv = dtid - py * CVc;
         const int jc = p.NB == 1 ? 0 : div_small(py, 1.0f / (float)p.PYc), pl = py - jc * p.PYc;   // crop of this lane, lane within the crop
@@ -485,10 +486,10 @@ __global__ void __maxnreg__(80) k1w_kernel(const __grid_constant__ K1WParams p) 
             k1w::arrive(b_r_full + 8 * buf);
         }
     }
-    if (tr && (warp == 0 || warp == 1 || warp == 4 || warp == 4 + 4 * EPI_WG)) {
+    if (tr && (warp == 0 || warp == 1 || warp == 4 || warp == 24 - 4 * EPI_WG)) {
         // trace row of this CTA: [0] total cycles, then per role (producer, MMA, epilogue warp 0, depthwise warp 0): its waits
         long long* row = p.trace + (long long)blockIdx.x * 16;
-        const int slot = warp == 0 ? 1 : (warp == 1 ? 4 : (warp == 4 ? 7 : 10));
+        const int slot = warp == 0 ? 1 : (warp == 1 ? 4 : (warp == 4 ? 10 : 7));
         row[slot] = tw0; row[slot + 1] = tw1; row[slot + 2] = clock64() - t_begin;
         if (warp == 0) row[0] = clock64() - t_begin;
     }

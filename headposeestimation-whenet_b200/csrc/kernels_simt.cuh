@@ -507,9 +507,20 @@ __device__ __forceinline__ void se_gate_fc(const float* mean, float* hid, const 
                                            int C, int Cse, float* gate_sm = nullptr) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    // The FMAs keep their sequential order (bitwise identical on every route); the weight LOADS of eight steps are issued
+    // together first - the serial chain of L2-latency loads was the whole cost of this kernel at C = 1152 (60 us / 512 crops).
     for (int j = warp; j < Cse; j += NT / 32) {
         float s = 0.f;
-        for (int c = lane; c < C; c += 32) s = fmaf(mean[c], w1t[(long long)j * C + c], s);
+        const float* wr = w1t + (long long)j * C;
+        int c = lane;
+        for (; c + 7 * 32 < C; c += 8 * 32) {
+            float wv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) wv[u] = wr[c + u * 32];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s = fmaf(mean[c + u * 32], wv[u], s);
+        }
+        for (; c < C; c += 32) s = fmaf(mean[c], wr[c], s);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) hid[j] = swish_f(s + b1[j]);
@@ -517,7 +528,16 @@ __device__ __forceinline__ void se_gate_fc(const float* mean, float* hid, const 
     __syncthreads();
     for (int c = tid; c < C; c += NT) {
         float s = b2[c];
-        for (int j = 0; j < Cse; ++j) s = fmaf(hid[j], w2[(long long)j * C + c], s);
+        const float* wc = w2 + c;
+        int j = 0;
+        for (; j + 7 < Cse; j += 8) {
+            float wv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) wv[u] = wc[(long long)(j + u) * C];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s = fmaf(hid[j + u], wv[u], s);
+        }
+        for (; j < Cse; ++j) s = fmaf(hid[j], wc[(long long)j * C], s);
         const float g = sigmoid_f(s);
         gate_n[c] = g;
         if (gate_sm) gate_sm[c] = g;      // may alias `mean`: the means are dead after the barrier above
