@@ -178,7 +178,7 @@ __global__ void __maxnreg__(80) k1w_kernel(const __grid_constant__ K1WParams p) 
     const int cbase = chunk * CC;
     const int n_epi_threads = 32 * p.n_epi;
     const bool tr = p.trace != nullptr && lane == 0;
-    long long tw0 = 0, tw1 = 0;                          // trace: cycles this thread spent in its waits
+    long long tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0, tn = 0; // trace: cycles this thread spent in its waits / sub-steps
     const long long t_begin = tr ? clock64() : 0;
 
     if (tid == 0) {
@@ -347,46 +347,62 @@ __global__ void __maxnreg__(80) k1w_kernel(const __grid_constant__ K1WParams p) 
             if (!*s_abort) {
                 const uint32_t e0 = sE + (uint32_t)buf * p.e_buf;
                 const uint32_t t0 = t_q + (uint32_t)(buf * p.tbuf_cols);
-                // (M tile, 16-column unit) pairs of this warp: f = grp, grp + NG, ... ; f -> (mt, u) advances without a division
-                auto process = [&](uint32_t (&r)[16], int mt, int u) {
-                    const bool box = mt == 0 ? in_box[0] : (mt == 1 ? in_box[1] : in_box[2]);
-                    const bool img = mt == 0 ? in_img[0] : (mt == 1 ? in_img[1] : in_img[2]);
-                    const uint32_t dst = e0 + (mt == 0 ? r_e[0] : (mt == 1 ? r_e[1] : r_e[2])) + u * 32;
-                    if (img) {
-                        uint32_t o[8];
+                // (M tile, 16-column unit) pairs of this warp: f = grp, grp + NG, ... ; f -> (mt, u) advances without a division.
+                // Two units are loaded and processed TOGETHER: with one or two epilogue warps per scheduler nothing hides the
+                // LDS -> FADD2 -> MUFU -> FFMA2 -> F2FP -> STS chain of one value but the other values of the same warp, and one
+                // unit gave ptxas four independent groups only (role trace: ~700 cycles per unit for ~70 instructions).
+                auto stage = [&](const uint32_t (&r)[16], int mt, int u, int j, float2 (&h)[2], bool& img, uint32_t& dst) {
+                    img = mt == 0 ? in_img[0] : (mt == 1 ? in_img[1] : in_img[2]);
+                    dst = e0 + (mt == 0 ? r_e[0] : (mt == 1 ? r_e[1] : r_e[2])) + u * 32;
+                    const float4 sh = lds_f4(sC + (uint32_t)(u * 16 + j * 4) * 4);
+                    h[0] = k1w::fadd2(make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), make_float2(sh.x, sh.y));
+                    h[1] = k1w::fadd2(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), make_float2(sh.z, sh.w));
+                };
+                auto process2 = [&](const uint32_t (&ra)[16], int mta, int ua, const uint32_t (&rb)[16], int mtb, int ub, bool have_b) {
+                    uint32_t oa[8], ob[8];
+                    bool ia = false, ib = false;
+                    uint32_t da = 0, db = 0;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 sh = lds_f4(sC + (uint32_t)(u * 16 + j * 4) * 4);
-                            const float2 a = k1w::swish2_from_half(k1w::fadd2(make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), make_float2(sh.x, sh.y)));
-                            const float2 b = k1w::swish2_from_half(k1w::fadd2(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), make_float2(sh.z, sh.w)));
-                            o[2 * j] = pack2<T>(a.x, a.y);
-                            o[2 * j + 1] = pack2<T>(b.x, b.y);
-                        }
-                        sts128(dst, make_uint4(o[0], o[1], o[2], o[3]));
-                        sts128(dst + 16, make_uint4(o[4], o[5], o[6], o[7]));
-                    } else if (box) {
-                        // halo pixel outside the image (or crop past the batch): the depthwise pads the EXPANDED tensor with zeros
-                        sts128(dst, zero);
-                        sts128(dst + 16, zero);
+                    for (int j = 0; j < 4; ++j) {
+                        float2 ha[2], hb[2];
+                        stage(ra, mta, ua, j, ha, ia, da);
+                        stage(rb, mtb, ub, j, hb, ib, db);
+                        const float2 a0 = k1w::swish2_from_half(ha[0]), b0 = k1w::swish2_from_half(hb[0]);
+                        const float2 a1 = k1w::swish2_from_half(ha[1]), b1 = k1w::swish2_from_half(hb[1]);
+                        oa[2 * j] = pack2<T>(a0.x, a0.y); oa[2 * j + 1] = pack2<T>(a1.x, a1.y);
+                        ob[2 * j] = pack2<T>(b0.x, b0.y); ob[2 * j + 1] = pack2<T>(b1.x, b1.y);
+                    }
+                    const bool boxa = mta == 0 ? in_box[0] : (mta == 1 ? in_box[1] : in_box[2]);
+                    const bool boxb = have_b && (mtb == 0 ? in_box[0] : (mtb == 1 ? in_box[1] : in_box[2]));
+                    // halo pixels outside the image (or crops past the batch): the depthwise pads the EXPANDED tensor with zeros
+                    if (boxa) {
+                        sts128(da, ia ? make_uint4(oa[0], oa[1], oa[2], oa[3]) : zero);
+                        sts128(da + 16, ia ? make_uint4(oa[4], oa[5], oa[6], oa[7]) : zero);
+                    }
+                    if (boxb) {
+                        sts128(db, ib ? make_uint4(ob[0], ob[1], ob[2], ob[3]) : zero);
+                        sts128(db + 16, ib ? make_uint4(ob[4], ob[5], ob[6], ob[7]) : zero);
                     }
                 };
                 uint32_t ra[16], rb[16];
                 int mt = 0, u = grp;
                 if (u >= units) { u -= units; ++mt; }                  // NG <= 2: at most one wrap
                 auto advance = [&](int& m, int& uu) { uu += NG; if (uu >= units) { uu -= units; ++m; } };
-                if (mt < mt_count) tmem_ld16_issue(t0 + (uint32_t)(mt * CC + u * 16), ra);
                 while (mt < mt_count) {
-                    tmem_ld16_wait(ra);
                     int mt2 = mt, u2 = u;
                     advance(mt2, u2);
-                    if (mt2 < mt_count) tmem_ld16_issue(t0 + (uint32_t)(mt2 * CC + u2 * 16), rb);     // flies while ra is processed
-                    process(ra, mt, u);
-                    if (mt2 >= mt_count) break;
+                    const bool have_b = mt2 < mt_count;
+                    tmem_ld16_issue(t0 + (uint32_t)(mt * CC + u * 16), ra);
+                    tmem_ld16_issue(t0 + (uint32_t)((have_b ? mt2 : mt) * CC + (have_b ? u2 : u) * 16), rb);
+                    long long tq = tr ? clock64() : 0;
+                    tmem_ld16_wait(ra);
                     tmem_ld16_wait(rb);
+                    if (tr) tw2 += clock64() - tq;
+                    tq = tr ? clock64() : 0;
+                    process2(ra, mt, u, rb, have_b ? mt2 : mt, have_b ? u2 : u, have_b);
+                    if (tr) { tw3 += clock64() - tq; tn += have_b ? 2 : 1; }
                     mt = mt2; u = u2;
                     advance(mt, u);
-                    if (mt < mt_count) tmem_ld16_issue(t0 + (uint32_t)(mt * CC + u * 16), ra);
-                    process(rb, mt2, u2);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -491,6 +507,7 @@ __global__ void __maxnreg__(80) k1w_kernel(const __grid_constant__ K1WParams p) 
         long long* row = p.trace + (long long)blockIdx.x * 16;
         const int slot = warp == 0 ? 1 : (warp == 1 ? 4 : (warp == 4 ? 10 : 7));
         row[slot] = tw0; row[slot + 1] = tw1; row[slot + 2] = clock64() - t_begin;
+        if (warp == 24 - 4 * EPI_WG) { row[13] = tw2; row[14] = tw3; row[15] = tn; }      // epilogue: in tcgen05.wait::ld, in process(), units
         if (warp == 0) row[0] = clock64() - t_begin;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -20,6 +20,7 @@ for blk in [int(b) for b in os.environ.get("BLOCKS", "2,3,4,5,6,7,9,10,12,13,16"
     t = t[t[:, 0] > 0]
     tot = np.median(t[:, 0])
     pct = lambda c: 100.0 * np.median(t[:, c] / np.maximum(t[:, 0], 1))
-    print("b%02d   %8.1f |  %5.1f%%               |  %5.1f%%   %5.1f%%          |  %5.1f%%   %5.1f%%              |  %5.1f%%   %5.1f%%" %
-          (blk, tot / 1e3, pct(1), pct(4), pct(5), pct(7), pct(8), pct(10), pct(11)), flush=True)
+    units = np.maximum(np.median(t[:, 15]), 1)
+    print("b%02d   %8.1f |  %5.1f%%               |  %5.1f%%   %5.1f%%          |  %5.1f%%   %5.1f%%              |  %5.1f%%   %5.1f%%   | epilogue warp: %d units, %.0f cyc/unit in wait::ld, %.0f cyc/unit in process" %
+          (blk, tot / 1e3, pct(1), pct(4), pct(5), pct(7), pct(8), pct(10), pct(11), units, np.median(t[:, 13]) / units, np.median(t[:, 14]) / units), flush=True)
 m.set_option("k1w_trace", 0)

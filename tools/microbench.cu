@@ -133,6 +133,42 @@ static void run(const char* name, double ops_per_thread_iter, float* d_out, u64*
            cudaGetErrorString(cudaGetLastError()));
 }
 
+// single-warp dependent chains: latency of one op (cycles per link)
+template <int MODE>
+__global__ void latency_probe(float* out, u64* cyc, float seed) {
+    __shared__ float sm[64];
+    sm[threadIdx.x] = seed * threadIdx.x;
+    __syncthreads();
+    float v = seed * (float)(threadIdx.x + 1);
+    float2 w = make_float2(v, -v);
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sm);
+    const u64 t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < 256; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (MODE == 0) v = tanh_approx(v);
+            else if (MODE == 1) v = fmaf(v, 0.999f, seed);
+            else if (MODE == 2) ffma2(w, w, make_float2(0.999f, 1.001f));
+            else if (MODE == 3) { uint32_t a; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(a) : "r"(sa + (__float_as_uint(v) & 0x7c))); v = __uint_as_float(a); }
+            else if (MODE == 4) { uint32_t r; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v), "f"(v)); v = __uint_as_float(r << 16); }
+            else if (MODE == 5) v = ex2_approx(v);
+        }
+    }
+    const u64 t1 = clock64();
+    out[threadIdx.x] = v + w.x;
+    if (threadIdx.x == 0) cyc[0] = t1 - t0;
+}
+template <int MODE>
+static void run_lat(const char* name, float* d_out, u64* d_cyc) {
+    latency_probe<MODE><<<1, 32>>>(d_out, d_cyc, 1e-3f);
+    cudaDeviceSynchronize();
+    latency_probe<MODE><<<1, 32>>>(d_out, d_cyc, 1e-3f);
+    cudaDeviceSynchronize();
+    u64 c = 0; cudaMemcpy(&c, d_cyc, sizeof(u64), cudaMemcpyDeviceToHost);
+    printf("latency %-40s %6.1f cycles per dependent op\n", name, (double)c / (256.0 * 8.0));
+}
+
 int main() {
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     const int ctas = sms * 2;
@@ -152,5 +188,11 @@ int main() {
     run<10>("tanh x8 + FFMA2 x8 interleaved (ops = tanh)", 8, d_out, d_cyc, ctas);
     run<11>("LDS.128 (ops = loads)", 8, d_out, d_cyc, ctas);
     run<12>("cvt.rn.bf16x2 (ops = cvts)", 8, d_out, d_cyc, ctas);
+    run_lat<0>("MUFU.TANH", d_out, d_cyc);
+    run_lat<5>("MUFU.EX2", d_out, d_cyc);
+    run_lat<1>("FFMA", d_out, d_cyc);
+    run_lat<2>("FFMA2", d_out, d_cyc);
+    run_lat<3>("LDS.32 (address dependent)", d_out, d_cyc);
+    run_lat<4>("F2FP.BF16 pack + shift", d_out, d_cyc);
     return 0;
 }
