@@ -10,17 +10,23 @@ from __future__ import annotations
 import numpy as np
 
 
-def enlarge_box(bbox, height: int, width: int):
-    """(y_min, x_min, y_max, x_max) from the detector -> integer slice bounds (y0, y1, x0, x1).
+def enlarge_bounds(bbox, height: int, width: int):
+    """(y_min, x_min, y_max, x_max) from the detector -> the margin-enlarged FLOAT bounds (y_min, y_max, x_min, x_max).
 
     The reference updates ``y_min`` / ``x_min`` first and then uses the UPDATED value for the far side
-    (demo_video.py:15-18); reproduced as is."""
+    (demo_video.py:15-18); reproduced as is.  The overlay (demo_video.py:25-29) uses these before truncation."""
     y_min, x_min, y_max, x_max = [np.float32(v) for v in bbox]
     y_min = max(0, y_min - abs(y_min - y_max) / 10)
     y_max = min(height, y_max + abs(y_min - y_max) / 10)
     x_min = max(0, x_min - abs(x_min - x_max) / 5)
     x_max = min(width, x_max + abs(x_min - x_max) / 5)
     x_max = min(x_max, width)
+    return y_min, y_max, x_min, x_max
+
+
+def enlarge_box(bbox, height: int, width: int):
+    """... truncated to the integer slice bounds (y0, y1, x0, x1) of demo_video.py:21."""
+    y_min, y_max, x_min, x_max = enlarge_bounds(bbox, height, width)
     return int(y_min), int(y_max), int(x_min), int(x_max)
 
 
