@@ -22,6 +22,7 @@
 #include "kernels_crop.cuh"
 #include "kernels_k1p.cuh"
 #include "kernels_k1w.cuh"
+#include "kernels_k2.cuh"
 #include <cudaTypedefs.h>
 
 // The fused-kernel launchers are instantiated in their own translation units (inst_k1_bf16.cu, inst_k1_f16.cu, inst_k1x.cu)
@@ -133,6 +134,8 @@ struct whenet_ctx {
     int* h_tflag = nullptr; // mbarrier-timeout flag: mapped pinned host memory, raised by any tcgen05 kernel of this context
     int* d_tflag = nullptr; // ... its device address (kernel parameter)
     int dw_variant = 1;     // 0 = one output per thread, 1 = register-blocked strips
+    int pw_variant = 2;     // tensor-core 1x1 kernel: 2 = pw_tc2 (one tile per CTA, cp.async ring), 3 = K2 (persistent, TMA, warp-specialised)
+    std::map<TmapKey, CUtensorMap> tmaps2;  // K2 tensor maps: activations by (K, M, pointer), weights by (-N, K, pointer)
     int pw_stage_cap = 0, pw_smem_kb = 54, pw_min_ctas = 148;    // pw_tc2 ring: max stages (0 = up to 4) and per-CTA smem budget that trades depth for co-residency
     int stem_variant = 1;   // 0 = 4 threads / pixel straight from global, 1 = smem-tiled, weights in the constant bank
     whenet::StemParams stem_params{};
@@ -386,6 +389,34 @@ int launch_pw(whenet_ctx* c, const char* name, const T* A, const float* W, const
     const double flops = 2.0 * (double)M * K * N;
     Scope sc(c, name, bytes, flops);
     if constexpr (sizeof(T) == 2) {
+        if (c->use_tc && Wt16 && c->pw_variant == 3) {
+            whenet::tc::K2Params kp{};
+            size_t smem = 0;
+            if (whenet::tc::plan_k2(M, K, N, hw, gate != nullptr, c->precision == WHENET_PRECISION_BF16, &kp, &smem)) {
+                if (c->tmaps2.size() > 1024) c->tmaps2.clear();
+                const TmapKey ka{K, (int)M, (const void*)A}, kw{-N, K, Wt16};
+                auto ia = c->tmaps2.find(ka);
+                if (ia == c->tmaps2.end()) {
+                    CUtensorMap tm;
+                    int rc = make_tmap_w(&tm, A, (int)M, K, whenet::tc::BM, c->precision == WHENET_PRECISION_BF16);
+                    if (rc) return rc;
+                    ia = c->tmaps2.emplace(ka, tm).first;
+                }
+                auto iw = c->tmaps2.find(kw);
+                if (iw == c->tmaps2.end()) {
+                    CUtensorMap tm;
+                    int rc = make_tmap_w(&tm, Wt16, N, K, kp.n_tile, c->precision == WHENET_PRECISION_BF16);
+                    if (rc) return rc;
+                    iw = c->tmaps2.emplace(kw, tm).first;
+                }
+                kp.tmA = ia->second; kp.tmW = iw->second;
+                kp.bias = bias; kp.gate = gate; kp.resid = resid; kp.out = out; kp.tflag = c->d_tflag;
+                int rc = whenet::tc::launch_k2<T>(c->stream, kp, smem, swish, gate != nullptr, resid != nullptr, c->sm_count);
+                if (rc == 0) { CK(cudaGetLastError()); return 0; }
+                if (rc < 0) return fail(WHENET_ECUDA, "K2 launch failed for %s (rc=%d)", name, rc);
+            }
+            // shape or epilogue not covered by K2 -> pw_tc2 below
+        }
         if (c->use_tc && Wt16) {
             int rc = whenet::tc::launch_pw_tc2<T>(c->stream, c->d_tflag, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish, c->pw_stage_cap, c->pw_smem_kb, c->pw_min_ctas);
             if (rc == 0) { CK(cudaGetLastError()); return 0; }
@@ -849,6 +880,7 @@ int bind_packed(whenet_ctx* c, const float* arena, size_t n_f32, const uint16_t*
     c->layout = L;
     c->weights_loaded = true;
     c->tmaps.clear();
+    c->tmaps2.clear();
     drop_graphs(c);
     return 0;
 }
@@ -1259,6 +1291,14 @@ int debug_conv_impl(whenet_ctx* c, int use_tc, const float* A, const float* W, c
     if (use_tc) {
         rc = 1;
         if constexpr (sizeof(T) == 2)
+            if (use_tc == 3) {
+                const int saved_v = c->pw_variant;
+                c->pw_variant = 3;
+                c->tmaps2.clear();
+                rc = launch_pw<T>(c, "debug.conv1x1", dA, dW, dWt, dB, dG, dR, dO, M, K, N, hw, swish != 0);
+                c->pw_variant = saved_v;
+                c->tmaps2.clear();
+            } else
             rc = whenet::tc::launch_pw_tc2<T>(c->stream, c->d_tflag, dA, dWt, dB, dG, dR, dO, M, K, N, hw, swish != 0);
         if (rc == 0 && cudaGetLastError() != cudaSuccess) rc = -1;
         if (rc != 0) rc = fail(WHENET_EINVAL, "tensor-core family cannot run M=%lld K=%d N=%d (rc=%d)", M, K, N, rc);
@@ -1451,6 +1491,7 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!strcmp(key, "stem_variant")) { c->stem_variant = value; return 0; }
     if (!strcmp(key, "k1_variant")) { c->k1_variant = value; return 0; }
     if (!strcmp(key, "dw1_fused")) { c->dw1_fused = value; return 0; }
+    if (!strcmp(key, "pw_variant")) { c->pw_variant = value; return 0; }
     if (!strcmp(key, "pw_stage_cap")) { c->pw_stage_cap = value; return 0; }
     if (!strcmp(key, "pw_smem_kb")) { c->pw_smem_kb = value; return 0; }
     if (!strcmp(key, "pw_min_ctas")) { c->pw_min_ctas = value; return 0; }

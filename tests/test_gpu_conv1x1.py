@@ -1,4 +1,5 @@
-"""The 1x1-convolution kernels alone, every (K, N) pair of the network, both kernel families.
+"""The 1x1-convolution kernels alone, every (K, N) pair of the network: CUDA-core (use_tc=0), pw_tc2 (2: one tile per
+CTA, cp.async ring) and K2 (3: persistent, TMA, warp-specialised).
 
 Reference for both families: numpy float64 on the SAME 16-bit-rounded inputs, so the only
 differences are fp32 accumulation order and the final rounding to the storage type."""
@@ -34,7 +35,7 @@ def net():
     m.close()
 
 
-@pytest.mark.parametrize("use_tc", [0, 2])
+@pytest.mark.parametrize("use_tc", [0, 2, 3])
 @pytest.mark.parametrize("K,N,kind", _layer_shapes())
 def test_conv1x1_shapes(net, use_tc, K, N, kind):
     rng = np.random.default_rng(K * 1000 + N)
@@ -96,12 +97,12 @@ def test_conv1x1_tc_row_tails(net, M):
     W = _bf16_round(rng.standard_normal((K, N)) / np.sqrt(K))
     bias = np.zeros(N, np.float32)
     b = net.debug_conv1x1(A, W, bias, use_tc=0)
-    for fam in (2,):
+    for fam in (2, 3):
         a = net.debug_conv1x1(A, W, bias, use_tc=fam)
         assert np.abs(a - b).max() <= 2.0 ** -6 * max(1.0, np.abs(b).max())
 
 
-@pytest.mark.parametrize("use_tc", [0, 2])
+@pytest.mark.parametrize("use_tc", [0, 2, 3])
 @pytest.mark.parametrize("K,N", [(480, 80), (1152, 192)])
 def test_conv1x1_residual_without_gate(net, use_tc, K, N):
     """Project conv of a block whose depthwise output was already gated by K1's tail: bias + residual, no gate."""
@@ -114,3 +115,31 @@ def test_conv1x1_residual_without_gate(net, use_tc, K, N):
     got = net.debug_conv1x1(A, W, bias, gate=None, resid=resid, hw=49, swish=False, use_tc=use_tc)
     ref = A.astype(np.float64) @ W.astype(np.float64) + bias + resid
     assert np.abs(got - ref).max() <= 2.5e-2 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("K,N,hw,res", [(96, 24, 3136, False), (240, 40, 784, True), (480, 80, 196, True), (1152, 192, 49, True),
+                                        (1152, 320, 49, False), (320, 1280, 49, None)])
+def test_k2_persistent_many_tiles(net, K, N, hw, res):
+    """K2 with more tiles than CTAs (every CTA loops over several tiles: ring wrap-around, both TMEM accumulators, gate rows
+    reloaded when a tile changes crop), resident and streamed weights, two n tiles (N = 320) and the swish head conv (N = 1280)."""
+    rng = np.random.default_rng(K + N)
+    M = 2 * 148 * 128 + 3 * 128 + 77
+    A = _bf16_round(rng.standard_normal((M, K)))
+    W = _bf16_round(rng.standard_normal((K, N)) / np.sqrt(K))
+    bias = rng.standard_normal(N).astype(np.float32)
+    head = res is None
+    gate = None if head else rng.uniform(0.1, 1.0, ((M + hw - 1) // hw, K)).astype(np.float32)
+    resid = _bf16_round(rng.standard_normal((M, N))) if res else None
+    got = net.debug_conv1x1(A, W, bias, gate=gate, resid=resid, hw=hw, swish=head, use_tc=3)
+    Ag = A.astype(np.float64)
+    if gate is not None:
+        Ag = _bf16_round(Ag * np.repeat(gate, hw, axis=0)[:M]).astype(np.float64)
+    ref = Ag @ W.astype(np.float64) + bias
+    if head:
+        ref = ref / (1.0 + np.exp(-ref))
+    if resid is not None:
+        ref = ref + resid
+    err = np.abs(got - ref).max() / max(1.0, np.abs(ref).max())
+    assert err <= 2.0 ** -7, err
+    two = net.debug_conv1x1(A, W, bias, gate=gate, resid=resid, hw=hw, swish=head, use_tc=2)
+    assert np.abs(got - two).max() <= 2.0 ** -6 * max(1.0, np.abs(ref).max())
