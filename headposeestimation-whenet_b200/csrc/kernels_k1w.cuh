@@ -74,14 +74,16 @@ namespace k1w {
 // Bounded wait on a barrier given by its shared-memory address.  The loop body is try_wait + branch (ncu showed the
 // re-poll loop of the first version at 16-22 % of all issued instructions, taken from the warps that had work); the abort
 // flag is looked at every 64 polls only.  A protocol bug ends in the timeout flag instead of a hung GPU.
+// No suspend-time hint: with one, ptxas emits NANOSLEEP.SYNCS and the wake-up after the arrive was measured to cost the
+// waiting role far more than the polls it saves (K2: 1.9 us per 128-row tile of a K = 32 layer).
 __device__ __forceinline__ void wait(uint32_t bar_addr, uint32_t parity, volatile int* abort_flag, int* tflag) {
-    for (uint32_t outer = 0; outer < (1u << 16); ++outer) {
+    for (uint32_t outer = 0; outer < (1u << 18); ++outer) {
         uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
             "mov.u32 n, 64;\n"
             "K1W_POLL_%=:\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 1000000;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "@p bra K1W_DONE_%=;\n\t"
             "sub.u32 n, n, 1;\n\t"
             "setp.ne.u32 p, n, 0;\n\t"
@@ -105,6 +107,13 @@ __device__ __forceinline__ void wait_t(uint32_t bar_addr, uint32_t parity, volat
 }
 __device__ __forceinline__ void arrive(uint32_t bar_addr) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+// One arrival per WARP: __syncwarp orders the lanes' shared-memory accesses before lane 0's (releasing) arrive.  Per-thread
+// arrives are 32 serialised shared-memory atomics per warp on one word; with 20+ warps signalling 4-5 barriers per item they
+// kept the LSU busy for more than a thousand cycles per item.
+__device__ __forceinline__ void arrive_warp(uint32_t bar_addr) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) arrive(bar_addr);
 }
 __device__ __forceinline__ void arrive_expect_tx(uint32_t bar_addr, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
@@ -186,11 +195,11 @@ __global__ void __maxnreg__(80) k1w_kernel(const __grid_constant__ K1WParams p) 
             tc::mbar_init(&bars[0 + i], 1);
             tc::mbar_init(&bars[2 + i], 1);
             tc::mbar_init(&bars[4 + i], 1);
-            tc::mbar_init(&bars[6 + i], n_epi_threads);
-            tc::mbar_init(&bars[8 + i], n_epi_threads);
-            tc::mbar_init(&bars[10 + i], p.n_dw);
-            tc::mbar_init(&bars[13 + i], p.n_dw);
-            tc::mbar_init(&bars[15 + i], 64);
+            tc::mbar_init(&bars[6 + i], p.n_epi);          // counts are WARPS (arrive_warp)
+            tc::mbar_init(&bars[8 + i], p.n_epi);
+            tc::mbar_init(&bars[10 + i], p.n_dw >> 5);
+            tc::mbar_init(&bars[13 + i], p.n_dw >> 5);
+            tc::mbar_init(&bars[15 + i], 2);
         }
         tc::mbar_init(&bars[12], 1);
         s_abort_mem = 0;
@@ -290,7 +299,7 @@ __global__ void __maxnreg__(80) k1w_kernel(const __grid_constant__ K1WParams p) 
                 if (n0 + jj < p.N)
                     p.partial[((long long)(n0 + jj) * p.tiles + it.t) * p.Cexp + cbase + cc] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
             }
-            k1w::arrive(b_r_empty + 8 * buf);
+            k1w::arrive_warp(b_r_empty + 8 * buf);
         }
       }
     } else if (warp >= 24 - 4 * EPI_WG) {
@@ -406,8 +415,8 @@ __global__ void __maxnreg__(80) k1w_kernel(const __grid_constant__ K1WParams p) 
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            k1w::arrive(b_t_empty + 8 * buf);
-            k1w::arrive(b_e_full + 8 * buf);
+            k1w::arrive_warp(b_t_empty + 8 * buf);
+            k1w::arrive_warp(b_e_full + 8 * buf);
         }
     } else {
         if (EPI_WG == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
@@ -493,13 +502,13 @@ __global__ void __maxnreg__(80) k1w_kernel(const __grid_constant__ K1WParams p) 
                     }
                 }
             }
-            k1w::arrive(b_e_empty + 8 * buf);                 // every depthwise thread: its reads of this E are done
+            k1w::arrive_warp(b_e_empty + 8 * buf);            // this warp's reads of this E are done
             // squeeze partial sums of the item: this lane's sums -> ring slot; the reducer warps take it from there
             k1w::wait_t(b_r_empty + 8 * buf, ((k >> 1) & 1) ^ 1, s_abort, p.tflag, tr, tw1);
             if (lane_ok)
                 asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sR + (uint32_t)((buf * p.PY + py) * CC + cv * 4) * 4),
                              "f"(sum01.x), "f"(sum01.y), "f"(sum23.x), "f"(sum23.y) : "memory");
-            k1w::arrive(b_r_full + 8 * buf);
+            k1w::arrive_warp(b_r_full + 8 * buf);
         }
     }
     if (tr && (warp == 0 || warp == 1 || warp == 4 || warp == 24 - 4 * EPI_WG)) {

@@ -68,12 +68,12 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
     if (tid == 0) {
         for (int i = 0; i < 8; ++i) {
             mbar_init(&bars[i], 1);
-            mbar_init(&bars[8 + i], kGateThreads);
+            mbar_init(&bars[8 + i], kGateThreads / 32);     // counts are WARPS (arrive_warp)
             mbar_init(&bars[16 + i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars[24 + i], 1);
-            mbar_init(&bars[26 + i], 128);
+            mbar_init(&bars[26 + i], 4);
         }
         mbar_init(&bars[28], 1);
         s_abort_mem = 0;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            k1w::arrive(b_t_empty + 8 * tb);
+            k1w::arrive_warp(b_t_empty + 8 * tb);
         }
     } else if (GATE && warp >= 8) {
         // =========================================================================== gate: A stage <- A stage * gate[crop(row)]
@@ -223,11 +223,17 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
                 asm volatile("bar.sync 1, %0;" ::"n"(kGateThreads) : "memory");
                 crop0_loaded = ncrops > 1 ? -1 : crop0;
             }
+            // gate row of each of this thread's four tile rows: (m0 + r) / hw - crop0 without an integer division per row
+            // (r + offset-in-crop < 128 + hw: the float reciprocal is exact for these small numbers)
             uint32_t g_row[4];
+            {
+                const int off = m0 - crop0 * p.hw;
+                const float inv_hw = 1.0f / (float)p.hw;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = r0 + 32 * i;
-                g_row[i] = r < rows_valid ? (uint32_t)(((m0 + r) / p.hw - crop0) * p.K) * 4u : 0u;
+                for (int i = 0; i < 4; ++i) {
+                    const int r = r0 + 32 * i;
+                    g_row[i] = r < rows_valid ? (uint32_t)(div_small(r + off, inv_hw) * p.K) * 4u : 0u;
+                }
             }
             for (int kb = 0; kb < p.nkb; ++kb, ++g) {
                 const int s = g % p.stages;
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
                             sts128_(a0 + i * 4096, scale8s<T>(lds128(a0 + i * 4096), sG + g_row[i] + (uint32_t)((kb * 8 + c) * 8) * 4));
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                k1w::arrive(b_ready + 8 * s);
+                k1w::arrive_warp(b_ready + 8 * s);
             }
         }
     }

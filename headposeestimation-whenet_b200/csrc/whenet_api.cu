@@ -23,6 +23,7 @@
 #include "kernels_k1p.cuh"
 #include "kernels_k1w.cuh"
 #include "kernels_k2.cuh"
+#include "kernels_tc32.cuh"
 #include <cudaTypedefs.h>
 
 // The fused-kernel launchers are instantiated in their own translation units (inst_k1_bf16.cu, inst_k1_f16.cu, inst_k1x.cu)
@@ -170,6 +171,7 @@ struct whenet_ctx {
     std::vector<BlockW> bw;
     float* d_arena = nullptr;
     void* d_arena16 = nullptr;
+    size_t split_lo_bytes = 0;     // fp32 mode: byte distance from a weight's bf16 hi part to its lo part in the 16-bit arena
     std::vector<int64_t> layout;   // offsets of every packed tensor inside the two arenas (the persisted artefact's index)
     float *w_stem = nullptr, *b_stem = nullptr, *lut = nullptr;
     float *w_head = nullptr, *b_head = nullptr, *w_fct = nullptr, *b_fc = nullptr;
@@ -422,6 +424,13 @@ int launch_pw(whenet_ctx* c, const char* name, const T* A, const float* W, const
             if (rc == 0) { CK(cudaGetLastError()); return 0; }
             if (rc < 0) return fail(WHENET_ECUDA, "tensor-core 1x1 launch failed for %s (rc=%d)", name, rc);
             // rc > 0: shape not supported by the tensor-core kernel -> CUDA-core kernel below
+        }
+    }
+    if constexpr (sizeof(T) == 4) {
+        if (c->use_tc && Wt16 && c->split_lo_bytes) {
+            int rc = whenet::tc::launch_pw_tc32(c->stream, c->d_tflag, A, Wt16, (const char*)Wt16 + c->split_lo_bytes, bias, gate, resid, out, M, K, N, hw, swish);
+            if (rc == 0) { CK(cudaGetLastError()); return 0; }
+            if (rc < 0) return fail(WHENET_ECUDA, "split-bf16 tensor-core 1x1 launch failed for %s (rc=%d)", name, rc);
         }
     }
     dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
@@ -836,7 +845,8 @@ int bind_packed(whenet_ctx* c, const float* arena, size_t n_f32, const uint16_t*
         return fail(WHENET_ESHAPE, "packed weights: bad index (size %zu, magic/version mismatch)", L.size());
     if (L[2] != c->precision) return fail(WHENET_ESHAPE, "packed weights were exported for precision %lld, this context is %d", (long long)L[2], c->precision);
     if ((size_t)L[3] != n_f32 || (size_t)L[4] != n_16 || (size_t)L[13] != nb) return fail(WHENET_ESHAPE, "packed weights: arena sizes do not match the index");
-    if ((c->precision != WHENET_PRECISION_FP32) != (n_16 > 0)) return fail(WHENET_ESHAPE, "packed weights: 16-bit arena does not fit the precision");
+    if (n_16 == 0) return fail(WHENET_ESHAPE, "packed weights: the 16-bit arena is missing");
+    c->split_lo_bytes = c->precision == WHENET_PRECISION_FP32 ? n_16 : 0;       // fp32: [hi | lo], n_16 / 2 elements each = n_16 bytes apart
     for (size_t i = 5; i < L.size(); ++i)
         if (i != 13 && (L[i] < 0 || (size_t)L[i] >= std::max(n_f32, n_16))) return fail(WHENET_ESHAPE, "packed weights: offset %zu out of range", i);
     if (c->d_arena) { cudaFree(c->d_arena); c->d_arena = nullptr; }
@@ -1115,7 +1125,17 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
 
     // ---- 16-bit arena in the storage type of this context
     std::vector<uint16_t> h16;
-    if (c->precision != WHENET_PRECISION_FP32) {
+    if (c->precision == WHENET_PRECISION_FP32) {
+        // parity mode on the tensor core (option tensor_cores=1): every K-major weight as bf16 hi | lo (x = hi + lo to 2^-18)
+        const size_t n = arena16src.size();
+        h16.resize(2 * n);
+        for (size_t i = 0; i < n; ++i) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(arena16src[i]);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(arena16src[i] - __bfloat162float(hi));
+            memcpy(&h16[i], &hi, 2);
+            memcpy(&h16[n + i], &lo, 2);
+        }
+    } else {
         h16.resize(arena16src.size());
         for (size_t i = 0; i < h16.size(); ++i) {
             if (c->precision == WHENET_PRECISION_BF16) { __nv_bfloat16 v = to16<__nv_bfloat16>(arena16src[i]); memcpy(&h16[i], &v, 2); }
@@ -1300,6 +1320,24 @@ int debug_conv_impl(whenet_ctx* c, int use_tc, const float* A, const float* W, c
                 c->tmaps2.clear();
             } else
             rc = whenet::tc::launch_pw_tc2<T>(c->stream, c->d_tflag, dA, dWt, dB, dG, dR, dO, M, K, N, hw, swish != 0);
+        uint16_t* dS = nullptr;
+        if constexpr (sizeof(T) == 4) {
+            // fp32 parity mode on the tensor core: bf16 hi | lo split of the K-major weights, as whenet_load_weights builds it
+            std::vector<uint16_t> hs((size_t)2 * N * K);
+            for (size_t i = 0; i < (size_t)N * K; ++i) {
+                const float wv = whenet_host_cvt_back(hWt[i]);
+                const __nv_bfloat16 hi = __float2bfloat16_rn(wv), lo = __float2bfloat16_rn(wv - __bfloat162float(hi));
+                memcpy(&hs[i], &hi, 2);
+                memcpy(&hs[(size_t)N * K + i], &lo, 2);
+            }
+            if (cudaMalloc(&dS, hs.size() * 2 + 256) == cudaSuccess) {
+                cudaMemcpyAsync(dS, hs.data(), hs.size() * 2, cudaMemcpyHostToDevice, c->stream);
+                cudaStreamSynchronize(c->stream);
+                rc = whenet::tc::launch_pw_tc32(c->stream, c->d_tflag, (const float*)dA, dS, dS + (size_t)N * K, dB, dG, (const float*)dR, (float*)dO, M, K, N, hw, swish != 0);
+                cudaStreamSynchronize(c->stream);
+                cudaFree(dS);
+            } else rc = -1;
+        }
         if (rc == 0 && cudaGetLastError() != cudaSuccess) rc = -1;
         if (rc != 0) rc = fail(WHENET_EINVAL, "tensor-core family cannot run M=%lld K=%d N=%d (rc=%d)", M, K, N, rc);
     } else {
@@ -1459,7 +1497,7 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!c || !key) return fail(WHENET_EINVAL, "bad arguments");
     drop_graphs(c);        // every option may change the launch sequence a captured graph froze
     c->cfg_epoch++;
-    if (!strcmp(key, "tensor_cores")) { c->use_tc = value && c->precision != WHENET_PRECISION_FP32; return 0; }
+    if (!strcmp(key, "tensor_cores")) { c->use_tc = value; return 0; }      // fp32: 1 = split-bf16 (3 MMAs per product) parity mode
     if (!strcmp(key, "streams")) { c->n_streams = value < 1 ? 1 : (value > 4 ? 4 : value); return 0; }
     if (!strcmp(key, "se_fused")) { c->se_fused = value; return 0; }
     if (!strcmp(key, "se_tail")) { c->se_tail = value; return 0; }

@@ -141,5 +141,40 @@ def test_k2_persistent_many_tiles(net, K, N, hw, res):
         ref = ref + resid
     err = np.abs(got - ref).max() / max(1.0, np.abs(ref).max())
     assert err <= 2.0 ** -7, err
-    two = net.debug_conv1x1(A, W, bias, gate=gate, resid=resid, hw=hw, swish=head, use_tc=2)
-    assert np.abs(got - two).max() <= 2.0 ** -6 * max(1.0, np.abs(ref).max())
+    if M % hw == 0 or hw < 784:        # pw_tc2 tiles gated layers per crop while H*W >= 784 and then needs whole crops
+        two = net.debug_conv1x1(A, W, bias, gate=gate, resid=resid, hw=hw, swish=head, use_tc=2)
+        assert np.abs(got - two).max() <= 2.0 ** -6 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("K,N,kind", [(16, 96, "expand"), (96, 24, "project"), (144, 24, "project_res"), (672, 192, "project"), (1152, 320, "project"), (320, 1280, "expand")])
+def test_conv1x1_fp32_split_bf16(K, N, kind):
+    """fp32 parity mode on the tensor core: x = hi + lo bf16 split, three MMAs per product, fp32 accumulation - against
+    float64 on the unrounded fp32 inputs (the CUDA-core fp32 kernel is the second reference)."""
+    import whenet_b200
+    m = whenet_b200.WHENet(None, device=0, precision="fp32", max_batch=8)
+    rng = np.random.default_rng(K + N)
+    hw = 49
+    M = 5 * hw + 17
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    gate = resid = None
+    swish = kind == "expand"
+    if kind.startswith("project"):
+        gate = rng.uniform(0.1, 1.0, ((M + hw - 1) // hw, K)).astype(np.float32)
+    if kind == "project_res":
+        resid = rng.standard_normal((M, N)).astype(np.float32)
+    got = m.debug_conv1x1(A, W, bias, gate=gate, resid=resid, hw=hw, swish=swish, use_tc=1)
+    simt = m.debug_conv1x1(A, W, bias, gate=gate, resid=resid, hw=hw, swish=swish, use_tc=0)
+    Ag = A.astype(np.float64)
+    if gate is not None:
+        Ag = (A * np.repeat(gate, hw, axis=0)[:M]).astype(np.float64)      # the product is formed in fp32 on the device
+    ref = Ag @ W.astype(np.float64) + bias
+    if swish:
+        ref = ref / (1.0 + np.exp(-ref))
+    if resid is not None:
+        ref = ref + resid
+    scale = max(1.0, np.abs(ref).max())
+    assert np.abs(got - ref).max() <= 3e-5 * scale, np.abs(got - ref).max()
+    assert np.abs(got - simt).max() <= 3e-5 * scale
+    m.close()

@@ -228,3 +228,36 @@ def test_packed_artefact_round_trip(prec, tmp_path, sample_crops, jitter_crops):
     stlite.save(bad, {"arena_f32": z["arena_f32"], "arena_16": z["arena_16"], "index": idx}, meta)
     with pytest.raises(whenet_b200.WhenetError):
         whenet_b200.WHENet(bad, device=0, precision=prec, max_batch=8)
+
+
+def test_fp32_tensor_core_parity_mode(oracle64, oracle32, sample_crops, jitter_crops, golden):
+    """fp32 storage, 1x1 convolutions on tcgen05 through the bf16 hi/lo split (3 MMAs per product): the north_star tolerance
+    (0.01 deg vs the float64 oracle) on tensor cores, every block boundary within 2e-4 relative of the float32 oracle,
+    and agreement with the CUDA-core fp32 kernels far below that."""
+    import whenet_b200
+    crops = np.concatenate([sample_crops, jitter_crops])
+    ref = np.array([[s["yaw"], s["pitch"], s["roll"]] for s in golden["samples"]] +
+                   list(zip(golden["jitter"]["yaw"], golden["jitter"]["pitch"], golden["jitter"]["roll"])))
+    m = whenet_b200.WHENet(SNAP, device=0, precision="fp32", max_batch=64)
+    simt = np.stack(m.get_angle(crops), axis=1)
+    n0 = m.launch_count()
+    m.set_option("tensor_cores", 1)
+    taps = {}
+    oracle32.get_angle(crops[:2], taps)
+    m.enable_taps(True)
+    m.get_angle(crops[:2])
+    m.enable_taps(False)
+    for nm in ["stem"] + ["block%d" % i for i in range(1, 17)] + ["head", "pooled"]:
+        r = taps[nm].astype(np.float64).reshape(-1)
+        g = m.tap(nm).astype(np.float64)
+        e = float(np.abs(g - r).max() / (np.abs(r).max() + 1e-30))
+        assert e < 2e-4, (nm, e)
+    got = np.stack(m.get_angle(crops), axis=1)
+    err = np.abs(got - ref).max()
+    print("fp32 tensor-core (split-bf16) mode: max |angle - oracle64| = %.5f deg, vs CUDA-core fp32 kernels %.5f deg" % (err, np.abs(got - simt).max()))
+    assert err <= 0.01
+    assert np.abs(got - simt).max() <= 5e-3
+    big = np.concatenate([crops] * 8)
+    many = np.stack(m.get_angle(big), axis=1)
+    assert np.array_equal(many[:8], got)            # batch invariant as well
+    m.close()
