@@ -194,7 +194,10 @@ def main():
     got = np.stack(net.get_angle(chk), axis=1)
     net.set_option("fused", 0); net.set_option("tensor_cores", 0); net.set_option("streams", 1)
     ref = np.stack(net.get_angle(chk), axis=1)
-    net.set_option("fused", 1); net.set_option("tensor_cores", 1); net.set_option("streams", 2)
+    net.set_option("fused", 1); net.set_option("tensor_cores", 0 if args.precision == "fp32" else 1); net.set_option("streams", 2)
+    for kv in args.opt:                                           # the self-check reset three switches: re-apply the overrides
+        k, v = kv.split("=")
+        net.set_option(k, int(v))
     tol = 0.02 if args.precision == "fp32" else (1.5 if args.precision == "bf16" else 0.3)
     self_check = float(np.abs(got - ref).max())
     if not (self_check <= tol):
