@@ -12,7 +12,7 @@ PRECISIONS = {"fp32": 0, "bf16": 1, "fp16": 2}
 EXPORTS = [
     "whenet_create", "whenet_load_weights", "whenet_export_packed", "whenet_import_packed", "whenet_set_stream", "whenet_forward_u8", "whenet_forward_u8_async", "whenet_forward_f32",
     "whenet_crop_resize_u8", "whenet_synchronize", "whenet_host_alloc", "whenet_host_free", "whenet_debug_enable_taps", "whenet_debug_tap",
-    "whenet_debug_conv1x1", "whenet_debug_decode", "whenet_debug_raise_timeout", "whenet_debug_read_trace", "whenet_debug_set_k1_plan", "whenet_debug_set_k1p_plan", "whenet_debug_set_k1w_plan", "whenet_profile_enable", "whenet_profile_read", "whenet_launch_count", "whenet_set_option",
+    "whenet_debug_conv1x1", "whenet_debug_decode", "whenet_debug_raise_timeout", "whenet_debug_read_trace", "whenet_debug_set_k1_plan", "whenet_debug_set_k1w_plan", "whenet_profile_enable", "whenet_profile_read", "whenet_launch_count", "whenet_set_option",
     "whenet_last_error", "whenet_version", "whenet_destroy",
 ]
 
@@ -79,7 +79,6 @@ def load():
     L.whenet_debug_raise_timeout.argtypes = [P]
     L.whenet_debug_read_trace.argtypes = [P, P, C.c_int]
     L.whenet_debug_set_k1_plan.argtypes = [P] + [C.c_int] * 7
-    L.whenet_debug_set_k1p_plan.argtypes = [P] + [C.c_int] * 6
     L.whenet_debug_set_k1w_plan.argtypes = [P] + [C.c_int] * 8
     L.whenet_profile_enable.argtypes = [P, C.c_int]
     L.whenet_profile_read.argtypes = [P, C.POINTER(KernelStat), C.c_int]

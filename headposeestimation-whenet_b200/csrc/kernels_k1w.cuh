@@ -40,7 +40,7 @@ struct alignas(64) K1WParams {
     CUtensorMap tmA;       // block input  [N][Hin][Hin][Cin]  (dims innermost first: C, W, H, N), box {64, IW, IH, NB}, SWIZZLE_128B
     CUtensorMap tmW;       // 0.5 * BN-folded expand weights [Cexp][Cin] K-major, box {64, CC}, SWIZZLE_128B
     const float* shift;    // [Cexp]        0.5 * BN shift of the expand conv
-    const float* w_dw;     // [KS*KS][Cexp] 0.5 * BN-folded depthwise weights
+    const void* w_dw16;    // half [KS*KS][Cexp] 0.5 * BN-folded depthwise weights / kDwScale (HFMA2 depthwise, see kernels_fused.cuh)
     const float* b_dw;     // [Cexp]        0.5 * BN shift of the depthwise conv
     void* out;             // T [N][Ho][Ho][Cexp]
     float* partial;        // [N][tiles][Cexp]
@@ -378,8 +378,8 @@ __global__ void __maxnreg__(80) k1w_kernel(const __grid_constant__ K1WParams p) 
                         stage(rb, mtb, ub, j, hb, ib, db);
                         const float2 a0 = k1w::swish2_from_half(ha[0]), b0 = k1w::swish2_from_half(hb[0]);
                         const float2 a1 = k1w::swish2_from_half(ha[1]), b1 = k1w::swish2_from_half(hb[1]);
-                        oa[2 * j] = pack2<T>(a0.x, a0.y); oa[2 * j + 1] = pack2<T>(a1.x, a1.y);
-                        ob[2 * j] = pack2<T>(b0.x, b0.y); ob[2 * j + 1] = pack2<T>(b1.x, b1.y);
+                        oa[2 * j] = pack2<__half>(a0.x, a0.y); oa[2 * j + 1] = pack2<__half>(a1.x, a1.y);
+                        ob[2 * j] = pack2<__half>(b0.x, b0.y); ob[2 * j + 1] = pack2<__half>(b1.x, b1.y);
                     }
                     const bool boxa = mta == 0 ? in_box[0] : (mta == 1 ? in_box[1] : in_box[2]);
                     const bool boxb = have_b && (mtb == 0 ? in_box[0] : (mtb == 1 ? in_box[1] : in_box[2]));
@@ -430,16 +430,20 @@ __global__ void __maxnreg__(80) k1w_kernel(const __grid_constant__ K1WParams p) 
         const int nstrips = p.TH << p.spr_log2;
         const uint32_t e_rowstride = (uint32_t)p.IW * pitchE;
         constexpr int NCOL = (R - 1) * S + KS;
-        // depthwise constants of this CTA's channels: { b_dw[CC], w_dw[KS*KS][CC] } fp32, staged once by this group
+        // depthwise constants of this CTA's channels: { b_dw[CC] fp32 | w_dw16[KS*KS][CC] fp16 }, staged once by this group
         {
-            float* cst = reinterpret_cast<float*>(smem_raw + (sC - tc::smem_u32(smem_raw))) + CC;
-            for (int i = dtid; i < (KS * KS + 1) * CC; i += p.n_dw) {
+            float* cb = reinterpret_cast<float*>(smem_raw + (sC - tc::smem_u32(smem_raw))) + CC;
+            __half* cw = reinterpret_cast<__half*>(cb + CC);
+            const __half* w16 = reinterpret_cast<const __half*>(p.w_dw16);
+            for (int i = dtid; i < CC; i += p.n_dw) cb[i] = p.b_dw[cbase + i];
+            for (int i = dtid; i < KS * KS * CC; i += p.n_dw) {
                 const int row = div_small(i, 1.0f / (float)CC), c = i - row * CC;
-                cst[i] = row == 0 ? p.b_dw[cbase + c] : p.w_dw[(long long)(row - 1) * p.Cexp + cbase + c];
+                cw[i] = w16[(long long)row * p.Cexp + cbase + c];
             }
             asm volatile("bar.sync 1, %0;" ::"r"(p.n_dw) : "memory");
         }
-        const uint32_t cst = sC + (uint32_t)CC * 4 + (uint32_t)cv * 16;         // this thread's column of the constants
+        const uint32_t cst = sC + (uint32_t)CC * 4 + (uint32_t)cv * 16;         // this thread's shift values
+        const uint32_t cst_h = sC + (uint32_t)CC * 8 + (uint32_t)cv * 8;          // ... and its column of the fp16 weights
         const int c0 = cbase + cv * 4;
         T* const out = reinterpret_cast<T*>(p.out);
         const long long crop_elems = (long long)p.Ho * p.Ho * p.Cexp;
@@ -456,17 +460,19 @@ __global__ void __maxnreg__(80) k1w_kernel(const __grid_constant__ K1WParams p) 
                 const uint32_t e_cv = sE + (uint32_t)buf * p.e_buf + (uint32_t)(jc * p.e_rows) * pitchE + (uint32_t)cv * 8;
                 for (int sidx = pl; sidx < nstrips; sidx += p.PYc) {
                     const int oyl = sidx >> p.spr_log2, oxl0 = (sidx - (oyl << p.spr_log2)) * R;
-                    float2 acc[R][2];
+                    // fp16 E, fp16 weights, HFMA2 running sums (no unpack instructions); sum * kDwScale + shift in fp32
+                    __half2 hacc[R][2];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) { acc[r][0] = make_float2(bq.x, bq.y); acc[r][1] = make_float2(bq.z, bq.w); }
+                    for (int r = 0; r < R; ++r) { hacc[r][0] = __float2half2_rn(0.f); hacc[r][1] = __float2half2_rn(0.f); }
                     uint32_t erow = e_cv + (uint32_t)(oyl * S) * e_rowstride + (uint32_t)(oxl0 * S) * pitchE;
 #pragma unroll
                     for (int ky = 0; ky < KS; ++ky) {
-                        float2 wr[KS][2];
+                        __half2 wr[KS][2];
 #pragma unroll
                         for (int kx = 0; kx < KS; ++kx) {
-                            const float4 wq = lds_f4(cst + (uint32_t)((1 + ky * KS + kx) * CC) * 4);
-                            wr[kx][0] = make_float2(wq.x, wq.y); wr[kx][1] = make_float2(wq.z, wq.w);
+                            uint32_t w0, w1;
+                            lds64(cst_h + (uint32_t)((ky * KS + kx) * CC) * 2, w0, w1);
+                            wr[kx][0] = *reinterpret_cast<__half2*>(&w0); wr[kx][1] = *reinterpret_cast<__half2*>(&w1);
                         }
                         uint32_t ea = erow;
 #pragma unroll
@@ -474,19 +480,25 @@ __global__ void __maxnreg__(80) k1w_kernel(const __grid_constant__ K1WParams p) 
                             uint32_t a, b;
                             lds64(ea, a, b);
                             ea += pitchE;
-                            float2 x01, x23;
-                            unpack2<T>(a, x01.x, x01.y);
-                            unpack2<T>(b, x23.x, x23.y);
+                            const __half2 x01 = *reinterpret_cast<__half2*>(&a), x23 = *reinterpret_cast<__half2*>(&b);
 #pragma unroll
                             for (int r = 0; r < R; ++r) {
                                 const int kx = col - r * S;          // compile-time after unrolling
                                 if (kx >= 0 && kx < KS) {
-                                    ffma2(acc[r][0], x01, wr[kx][0]);
-                                    ffma2(acc[r][1], x23, wr[kx][1]);
+                                    hacc[r][0] = __hfma2(x01, wr[kx][0], hacc[r][0]);
+                                    hacc[r][1] = __hfma2(x23, wr[kx][1], hacc[r][1]);
                                 }
                             }
                         }
                         erow += e_rowstride;
+                    }
+                    float2 acc[R][2];
+                    const float2 sc = make_float2(kDwScale, kDwScale);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        acc[r][0] = make_float2(bq.x, bq.y); acc[r][1] = make_float2(bq.z, bq.w);
+                        ffma2(acc[r][0], __half22float2(hacc[r][0]), sc);
+                        ffma2(acc[r][1], __half22float2(hacc[r][1]), sc);
                     }
                     T* dst = out_n + ((long long)(ty0 + oyl) * p.Ho + tx0 + oxl0) * p.Cexp + c0;
 #pragma unroll
@@ -568,7 +580,7 @@ inline bool plan_k1w_candidate(int Hin, int Ho, int Cin, int Cexp, int k, int s,
     p->a_tx = (uint32_t)p->nkb * p->rows * 128;                               // full boxes, zero fill included
     p->w_tx = (uint32_t)p->nkb * CC * 128;
     const uint32_t w_bytes = ((uint32_t)p->nkb * CC * 128 + 1023u) & ~1023u;
-    const uint32_t c_bytes = (uint32_t)((k * k + 2) * CC * 4 + 15) & ~15u;    // shift[CC] | b_dw[CC] | w_dw[k*k][CC]
+    const uint32_t c_bytes = (uint32_t)(2 * CC * 4 + k * k * CC * 2 + 15) & ~15u;    // shift[CC] | b_dw[CC] fp32 | w_dw16[k*k][CC] fp16
     p->e_buf = ((uint32_t)NB * p->e_rows * p->pitchE + 15u) & ~15u;
     const uint32_t r_bytes = 2u * p->PY * CC * 4;
     for (int na = 2; na >= 1; --na) {

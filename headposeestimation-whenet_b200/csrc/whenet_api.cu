@@ -20,7 +20,6 @@
 #include "kernels_tc.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_crop.cuh"
-#include "kernels_k1p.cuh"
 #include "kernels_k1w.cuh"
 #include "kernels_k2.cuh"
 #include "kernels_tc32.cuh"
@@ -32,7 +31,6 @@ namespace fused {
 #define WHENET_EXTERN_FUSED(T)                                                                            \
     extern template int launch_k1<T>(cudaStream_t, K1Params, int, int, int, int, size_t, int);            \
     extern template int launch_dw_only<T>(cudaStream_t, K1Params, size_t, int);                           \
-    extern template int launch_k1p<T>(cudaStream_t, K1PParams, int, int, int, size_t, int, int);                \
     extern template int launch_k1w<T>(cudaStream_t, K1WParams, int, int, int, int, size_t, int, int);
 WHENET_EXTERN_FUSED(__nv_bfloat16)
 WHENET_EXTERN_FUSED(__half)
@@ -107,10 +105,10 @@ struct BlockW {   // device pointers into the fp32 arena
     float* b_exp_h = nullptr;                     // 0.5 * BN shift of the expand conv (K1W)
     void* wt_exp_aug = nullptr;                   // 16-bit [cexp][cin+8]: 0.5*(weights | shift_hi | shift_lo) | 0... (K1)
     float *w_dw_h = nullptr, *b_dw_h = nullptr;   // 0.5 * depthwise weights / shift (K1)
+    void* w_dw16 = nullptr;                       // fp16 [k*k][cexp]: 0.5 * depthwise weights / kDwScale (HFMA2 depthwise of K1 / K1W)
 };
 
 struct K1Plan { bool valid = false; whenet::fused::K1Params p{}; int R = 0; int NT = 256; size_t smem = 0; };
-struct K1PPlan { bool valid = false; whenet::fused::K1PParams p{}; int R = 0; size_t smem = 0; };
 struct K1WPlan { bool valid = false; whenet::fused::K1WParams p{}; int R = 0, NT = 0; size_t smem = 0; };
 struct TmapKey {
     int block, n; const void* ptr;
@@ -155,16 +153,13 @@ struct whenet_ctx {
     std::vector<K1WPlan> k1w;  // k1_variant 4: weight-stationary persistent K1 (TMA-staged input tiles)
     std::map<TmapKey, CUtensorMap> tmaps;   // input tensor maps of K1W by (block, crops, buffer)
     std::vector<CUtensorMap> tmap_w;        // weight tensor maps of K1W by block
-    std::vector<K1PPlan> k1p;  // k1_variant 3: persistent warp-specialised K1 for the blocks with several tiles per crop
+  // k1_variant 3: persistent warp-specialised K1 for the blocks with several tiles per crop
     int sm_count = 148;
     int k1w_trace_block = 0;   // debug: the K1W launch of this block records where its roles wait (whenet_debug_read_trace)
     long long* d_trace = nullptr;
-    int k1p_epi_warps = 8;     // epilogue group of K1P: 4 or 8 warps (the depthwise group gets the other 10 or 6)
-    int k1p_min_crops = 8;     // below this a persistent grid cannot fill the SMs: K1 with its chunk split is used instead
     K1Plan dw1;                // block 1 (no expand): depthwise-only instance of K1
     int dw1_fused = 1;
-    int k1_variant = 1;        // 1 = K1 everywhere, 3 = K1P (persistent, warp-specialised) for the blocks with several tiles per crop,
-                               // 4 = K1W (weight-stationary persistent CTAs, TMA input tiles) for every block with an expand conv
+    int k1_variant = 1;        // 1 = K1, 4 = K1W (weight-stationary persistent CTAs, TMA input tiles) for every block with an expand conv
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     bool weights_loaded = false;
     std::vector<BlockCfg> blocks;
@@ -325,8 +320,6 @@ int ensure_ws(whenet_ctx* c) {
         if (pl.valid) part = std::max(part, (size_t)pl.p.tiles_x * pl.p.tiles_y * pl.p.Cexp);
     for (const K1WPlan& pl : c->k1w)
         if (pl.valid) part = std::max(part, (size_t)pl.p.tiles * pl.p.Cexp);
-    for (const K1PPlan& pl : c->k1p)          // persistent variant: its own tile shapes (tuning hook) size the partials too
-        if (pl.valid) part = std::max(part, (size_t)pl.p.tiles * pl.p.k.Cexp);
     if (c->dw1.valid) part = std::max(part, (size_t)c->dw1.p.tiles_x * c->dw1.p.tiles_y * c->dw1.p.Cexp);
     c->ws_io = io; c->ws_ex = ex; c->ws_dw = dw; c->ws_part = part;
     CK(cudaMalloc(&c->bufA, ch * io * es));
@@ -534,7 +527,7 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
                     it = c->tmaps.emplace(key, tm).first;
                 }
                 p.tmA = it->second; p.tmW = c->tmap_w[i];
-                p.shift = w.b_exp_h; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial; p.tflag = c->d_tflag;
+                p.shift = w.b_exp_h; p.w_dw16 = w.w_dw16; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial; p.tflag = c->d_tflag;
                 p.trace = nullptr;
                 if (c->k1w_trace_block == b.idx) {
                     if (!c->d_trace) CK(cudaMalloc(&c->d_trace, 256 * 16 * sizeof(long long)));
@@ -549,21 +542,9 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
                 CK(cudaGetLastError());
                 tiles = p.tiles;
                 did_k1 = true;
-            } else if (c->use_fused && c->k1_variant == 3 && c->k1p[i].valid && nb >= c->k1p_min_crops && b.idx <= c->fused_max_block) {
-                whenet::fused::K1PParams pp = c->k1p[i].p;
-                whenet::fused::K1Params& p = pp.k;
-                p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial; p.tflag = c->d_tflag;
-                snprintf(nm, sizeof nm, "b%02d.k1", b.idx);
-                Scope sc(c, nm, (double)nb * ((double)b.hin * b.hin * b.cin + (double)b.hout * b.hout * b.cexp) * sizeof(T),
-                         2.0 * nb * ((double)b.hin * b.hin * b.cin * b.cexp + (double)b.hout * b.hout * b.k * b.k * b.cexp));
-                int rc = whenet::fused::launch_k1p<T>(c->stream, pp, b.k, b.s, c->k1p[i].R, c->k1p[i].smem, nb, c->sm_count);
-                if (rc != 0) return fail(WHENET_ECUDA, "K1P launch failed for block %d (rc=%d)", b.idx, rc);
-                CK(cudaGetLastError());
-                tiles = pp.tiles;
-                did_k1 = true;
             } else if (c->use_fused && c->k1[i].valid && b.idx <= c->fused_max_block) {
                 whenet::fused::K1Params p = c->k1[i].p;
-                p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial; p.tflag = c->d_tflag;
+                p.in = cur; p.wt_aug = w.wt_exp_aug; p.w_dw = w.w_dw_h; p.w_dw16 = w.w_dw16; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial; p.tflag = c->d_tflag;
                 p.w_se1t = w.w_se1t; p.b_se1 = w.b_se1; p.w_se2 = w.w_se2; p.b_se2 = w.b_se2; p.gate = c->d_gate; p.Cse = b.cse;
                 se_in_k1 = c->se_fused && p.NB == 1;
                 p.se_counter = se_in_k1 ? c->d_se_counter : nullptr;
@@ -833,8 +814,8 @@ template <> __nv_bfloat16 to16<__nv_bfloat16>(float v) { return __float2bfloat16
 template <> __half to16<__half>(float v) { return __float2half_rn(v); }
 
 constexpr int64_t kPackMagic = 0x57484e3242323030LL;   // "WHN2B200"
-constexpr int64_t kPackVersion = 2;
-constexpr int kPackHeader = 14, kPackPerBlock = 17;
+constexpr int64_t kPackVersion = 3;
+constexpr int kPackHeader = 14, kPackPerBlock = 18;
 
 // Upload a packed weight image (fp32 arena + 16-bit arena + index) and point the context at it.  Shared by
 // whenet_load_weights (which has just built the image from the raw Keras tensors) and whenet_import_packed (which read it
@@ -886,6 +867,7 @@ int bind_packed(whenet_ctx* c, const float* arena, size_t n_f32, const uint16_t*
         w.w_proj = A + o[8]; w.b_proj = A + o[9];
         w.wt_proj = base16 ? base16 + o[11] * 2 : nullptr;
         w.w_dw_h = A + o[13]; w.b_dw_h = A + o[14];
+        w.w_dw16 = base16 ? base16 + o[17] * 2 : nullptr;
     }
     c->layout = L;
     c->weights_loaded = true;
@@ -930,7 +912,6 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
     c->blocks = make_blocks();
     c->bw.resize(c->blocks.size());
     c->k1.resize(c->blocks.size());
-    c->k1p.resize(c->blocks.size());
     c->k1w.resize(c->blocks.size());
     c->tmap_w.resize(c->blocks.size());
     if (precision != WHENET_PRECISION_FP32) {
@@ -953,12 +934,6 @@ int whenet_create(whenet_ctx** out, int device, int max_batch, int precision) {
                 whenet::fused::K1WChoice wc{};
                 pw.valid = whenet::fused::plan_k1w(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, precision == WHENET_PRECISION_BF16, &pw.p, &wc, &pw.smem);
                 pw.R = wc.r; pw.NT = wc.nt;
-            }
-            if (pl.valid && pl.p.tiles_x * pl.p.tiles_y > 1) {       // K1P: same tile, strip and chunk shape as the K1 plan
-                K1PPlan& pq = c->k1p[i];
-                pq.valid = whenet::fused::plan_k1p(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, precision == WHENET_PRECISION_BF16,
-                                                   pl.p.TH, pl.p.TW, pl.R, pl.p.CC, c->k1p_epi_warps, &pq.p, &pq.smem);
-                pq.R = pl.R;
             }
         }
     c->use_fused = precision != WHENET_PRECISION_FP32;
@@ -1002,7 +977,8 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
                                                   while (arena.size() % 4) arena.push_back(0.f); return off; };
     auto put16 = [&](const std::vector<float>& v) { size_t off = arena16src.size(); arena16src.insert(arena16src.end(), v.begin(), v.end());
                                                     while (arena16src.size() % 8) arena16src.push_back(0.f); return off; };
-    struct Off { size_t w_exp, b_exp, w_dw, b_dw, w_se1t, b_se1, w_se2, b_se2, w_proj, b_proj, t_exp, t_proj, t_aug, w_dw_h, b_dw_h, t_exp_h, b_exp_h; };
+    struct Off { size_t w_exp, b_exp, w_dw, b_dw, w_se1t, b_se1, w_se2, b_se2, w_proj, b_proj, t_exp, t_proj, t_aug, w_dw_h, b_dw_h, t_exp_h, b_exp_h, w_dw16; };
+    std::vector<std::pair<size_t, size_t>> force_f16;     // ranges of the 16-bit arena that are fp16 whatever the storage type
     // values of the augmented expand weights; shift columns are filled after 16-bit rounding of the high part
     std::vector<std::pair<size_t, float>> shift_lo_fix;   // (index in arena16src of the hi column, full-precision shift)
     std::vector<Off> offs(c->blocks.size());
@@ -1084,6 +1060,9 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
             for (float& v : w) v *= 0.5f;
             for (float& v : bb) v *= 0.5f;
             o.w_dw_h = put(w); o.b_dw_h = put(bb);
+            for (float& v : w) v *= 1.0f / whenet::fused::kDwScale;
+            o.w_dw16 = put16(w);
+            force_f16.push_back({o.w_dw16, w.size()});
         }
         {
             const std::string n1 = conv_name();
@@ -1141,6 +1120,8 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
             if (c->precision == WHENET_PRECISION_BF16) { __nv_bfloat16 v = to16<__nv_bfloat16>(arena16src[i]); memcpy(&h16[i], &v, 2); }
             else { __half v = to16<__half>(arena16src[i]); memcpy(&h16[i], &v, 2); }
         }
+        for (auto& rg : force_f16)
+            for (size_t i = rg.first; i < rg.first + rg.second; ++i) { __half v = to16<__half>(arena16src[i]); memcpy(&h16[i], &v, 2); }
         // lo part of every K1 shift: what the 16-bit rounding of the hi part lost
         for (auto& fx : shift_lo_fix) {
             float hi;
@@ -1158,7 +1139,7 @@ int whenet_load_weights(whenet_ctx* c, const whenet_tensor* tensors, int n_tenso
         const Off& o = offs[i];
         const bool e = c->blocks[i].has_expand;
         for (size_t v : {e ? o.w_exp : 0, e ? o.b_exp : 0, o.w_dw, o.b_dw, o.w_se1t, o.b_se1, o.w_se2, o.b_se2, o.w_proj, o.b_proj, e ? o.t_exp : 0, o.t_proj,
-                         e ? o.t_aug : 0, o.w_dw_h, o.b_dw_h, e ? o.t_exp_h : 0, e ? o.b_exp_h : 0})
+                         e ? o.t_aug : 0, o.w_dw_h, o.b_dw_h, e ? o.t_exp_h : 0, e ? o.b_exp_h : 0, o.w_dw16})
             layout.push_back((int64_t)v);
     }
     return bind_packed(c, arena.data(), arena.size(), h16.data(), h16.size(), layout);
@@ -1444,23 +1425,6 @@ int whenet_debug_set_k1w_plan(whenet_ctx* c, int block, int th, int tw, int r, i
     return 0;
 }
 
-int whenet_debug_set_k1p_plan(whenet_ctx* c, int block, int th, int tw, int r, int cc, int epi_warps) {
-    if (!c || block < 2 || block > (int)c->blocks.size()) return fail(WHENET_EINVAL, "bad block index");
-    if (c->precision == WHENET_PRECISION_FP32) return fail(WHENET_EINVAL, "K1P needs a 16-bit storage mode");
-    const BlockCfg& b = c->blocks[block - 1];
-    if (cc < 16 || cc > 128 || (cc & 15) || r < 1 || th < 1 || tw < 1) return fail(WHENET_EINVAL, "bad plan parameters");
-    if (!whenet::fused::k1_has_instance(b.k, b.s, r)) return fail(WHENET_EINVAL, "no K1P instantiation for k=%d s=%d r=%d", b.k, b.s, r);
-    K1PPlan pq;
-    pq.valid = whenet::fused::plan_k1p(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, c->precision == WHENET_PRECISION_BF16,
-                                       th, tw, r, cc, epi_warps, &pq.p, &pq.smem);
-    if (!pq.valid) return fail(WHENET_EINVAL, "K1P plan %dx%d r%d cc%d epi%d does not fit block %d", th, tw, r, cc, epi_warps, block);
-    pq.R = r;
-    c->k1p[block - 1] = pq;
-    c->cfg_epoch++;
-    free_ws(c);      // the squeeze-partials buffer depends on the tile count
-    return 0;
-}
-
 int whenet_profile_enable(whenet_ctx* c, int enable) {
     if (!c) return fail(WHENET_EINVAL, "null context");
     c->prof_on = enable != 0;
@@ -1503,25 +1467,7 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!strcmp(key, "se_tail")) { c->se_tail = value; return 0; }
     if (!strcmp(key, "se_scale_out")) { c->se_scale_out = value; return 0; }
     if (!strcmp(key, "k1_split_ctas")) { c->k1_split_ctas = value; return 0; }
-    if (!strcmp(key, "k1p_min_crops")) { c->k1p_min_crops = value; return 0; }
     if (!strcmp(key, "k1w_trace")) { c->k1w_trace_block = value; return 0; }
-    if (!strcmp(key, "k1p_epi_warps")) {
-        if (value != 4 && value != 8) return fail(WHENET_EINVAL, "k1p_epi_warps is 4 or 8");
-        c->k1p_epi_warps = value;
-        free_ws(c);                                             // the squeeze-partials buffer follows the K1P plans
-        for (size_t i = 0; i < c->blocks.size(); ++i) {       // re-plan: the strip-lane count depends on the group sizes
-            const BlockCfg& b = c->blocks[i];
-            const K1Plan& pl = c->k1[i];
-            K1PPlan& pq = c->k1p[i];
-            pq.valid = false;
-            if (pl.valid && pl.p.tiles_x * pl.p.tiles_y > 1) {
-                pq.valid = whenet::fused::plan_k1p(b.hin, b.hout, b.cin, b.cexp, b.k, b.s, b.pad, c->precision == WHENET_PRECISION_BF16,
-                                                   pl.p.TH, pl.p.TW, pl.R, pl.p.CC, value, &pq.p, &pq.smem);
-                pq.R = pl.R;
-            }
-        }
-        return 0;
-    }
     if (!strcmp(key, "se_wide")) { c->se_wide = value; return 0; }
     if (!strcmp(key, "host_chunk")) { if (value < 1) return fail(WHENET_EINVAL, "host_chunk must be >= 1"); c->host_chunk = value; return 0; }
     if (!strcmp(key, "graph")) { c->use_graph = value; if (!value) drop_graphs(c); return 0; }

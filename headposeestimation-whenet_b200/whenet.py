@@ -300,10 +300,6 @@ class WHENet:
         """Tuning hook for the weight-stationary variant (see whenet_debug_set_k1w_plan); False when the plan cannot run."""
         return self._L.whenet_debug_set_k1w_plan(self._h, block, th, tw, r, cc, nb, n_epi, nt) == 0
 
-    def set_k1p_plan(self, block: int, th: int, tw: int, r: int, cc: int, epi_warps: int = 8) -> bool:
-        """Tuning hook for the persistent variant (see whenet_debug_set_k1p_plan); False when the plan cannot run."""
-        return self._L.whenet_debug_set_k1p_plan(self._h, block, th, tw, r, cc, epi_warps) == 0
-
     def enable_profile(self, on: bool = True):
         check(self._L.whenet_profile_enable(self._h, int(on)))
 

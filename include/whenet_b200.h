@@ -166,10 +166,6 @@ int whenet_debug_read_trace(whenet_ctx* ctx, int64_t* out, int n_rows);
  * crops per item (2 only where one tile is the whole image), epilogue warps (4 or 8), threads per CTA (768). */
 int whenet_debug_set_k1w_plan(whenet_ctx* ctx, int block, int th, int tw, int r, int cc, int nb, int n_epi, int nt);
 
-/* Same for K1P (option "k1_variant" = 3; blocks with several tiles per crop): tile, strip and chunk shape plus the
- * size of the TMEM-epilogue warp group (4 or 8; the depthwise group gets the remaining warps of the 512-thread CTA). */
-int whenet_debug_set_k1p_plan(whenet_ctx* ctx, int block, int th, int tw, int r, int cc, int epi_warps);
-
 /* Time every kernel of the NEXT forwards with CUDA events. */
 int whenet_profile_enable(whenet_ctx* ctx, int enable);
 /* Read (and reset) the accumulated per-kernel statistics; returns the count written. */
@@ -182,13 +178,15 @@ int64_t whenet_launch_count(whenet_ctx* ctx);
  *   "chunk"          crops per pass through the network (default max_batch: one pass)
  *   "streams"        1..4 batch parts running concurrently on internal streams (default 2)
  *   "graph"          1: replay device-resident forwards from a captured CUDA graph (default 0)
- *   "tensor_cores"   0: CUDA-core kernels for every 1x1 conv, 1: tcgen05 (default 1 for bf16/fp16, fp32 is always 0)
+ *   "tensor_cores"   16-bit modes: 0 = CUDA-core kernels for every 1x1 conv, 1 = tcgen05 (default 1).
+ *                    fp32 mode: 0 = fp32 FMA kernels (default), 1 = the 1x1 convs on tcgen05 through the bf16 hi/lo split
+ *                    (three MMAs per product, fp32 accumulation: 6e-4 deg from the float64 oracle on the golden crops)
  *   "fused"          1: K1 (expand + depthwise fused, expanded tensor in shared memory) for blocks 2..fused_max_block
- *   "fused_max_block", "dw1_fused", "k1_variant" (2 = K1T, depthwise on the tensor core; 3 = K1P, persistent
- *   warp-specialised K1 for blocks 2-6), "k1p_epi_warps" (4 or 8), "k1p_min_crops", "k1_split_ctas", "k1t_max_block",
- *   "k0" (stem + block-1 depthwise fused), "se_fused", "se_tail" (K1 CTAs that hold whole crops compute the
- *   SE gate themselves, default 1), "se_variant", "se_wide",
- *   "pw_variant" (1 register-staged ring, 2 cp.async ring), "pw_stage_cap", "pw_smem_kb", "pw_min_ctas" (split N until the grid has this many CTAs),
+ *   "k1_variant"     1 = K1 (one tile per CTA), 4 = K1W (weight-stationary persistent CTAs, TMA input tiles, warp roles)
+ *   "pw_variant"     2 = pw_tc2 (one tile per CTA, cp.async ring), 3 = K2 (persistent, TMA, warp-specialised)
+ *   "fused_max_block", "dw1_fused", "k1_split_ctas", "k1w_trace" (block whose K1W launch records its role waits),
+ *   "se_fused", "se_tail" (K1 CTAs that hold whole crops compute the SE gate themselves, default 1), "se_scale_out", "se_wide",
+ *   "pw_stage_cap", "pw_smem_kb", "pw_min_ctas" (split N until the grid has this many CTAs),
  *   "dw_variant", "stem_variant", "host_chunk".
  * Unknown keys return WHENET_ENOTFOUND. */
 int whenet_set_option(whenet_ctx* ctx, const char* key, int value);

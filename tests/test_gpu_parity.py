@@ -236,27 +236,6 @@ def test_se_tail_paths_bitwise(prec, oracle32, sample_crops, jitter_crops):
     m.close()
 
 
-def test_k1p_persistent_variant_matches_k1(sample_crops, jitter_crops):
-    """K1P (k1_variant=3: persistent CTAs, loader / MMA / TMEM-epilogue / depthwise warp groups connected by mbarriers) runs
-    blocks 2-6 from 8 crops up.  Its depthwise outputs must equal K1's bit for bit (same arithmetic per output); the squeeze
-    sums associate differently (16 strip lanes instead of 21), so gates may differ in the last bit and angles by rounding."""
-    import whenet_b200
-    crops = np.concatenate([sample_crops, jitter_crops])[:8]
-    assert crops.shape[0] == 8
-    m = whenet_b200.WHENet(SNAP, device=0, precision="bf16", max_batch=8)
-    m.enable_taps(True)
-    ref = np.stack(m.get_angle(crops), axis=1)
-    ref_taps = {nm: m.tap(nm).copy() for i in range(2, 7) for nm in ("dw%d" % i, "gate%d" % i, "block%d" % i)}
-    m.set_option("k1_variant", 3)
-    got = np.stack(m.get_angle(crops), axis=1)
-    for i in range(2, 7):
-        assert np.array_equal(m.tap("dw%d" % i), ref_taps["dw%d" % i]), i
-        assert np.abs(m.tap("gate%d" % i) - ref_taps["gate%d" % i]).max() < 1e-5
-        assert _relerr(m.tap("block%d" % i).astype(np.float64), ref_taps["block%d" % i].astype(np.float64)) < 2e-2
-    assert np.abs(got - ref).max() < 0.25
-    m.close()
-
-
 def test_fused_k1_batch_invariance(sample_crops, jitter_crops):
     import whenet_b200
     crops = np.concatenate([sample_crops, jitter_crops] * 3)[:19]

@@ -125,29 +125,6 @@ def test_timeout_flag_reaches_every_sync_path(n, sample_crops, jitter_crops):
     m.close()
 
 
-def test_k1p_oracle_taps(oracle32, sample_crops, jitter_crops):
-    """The persistent warp-specialised K1 variant (blocks with several tiles per crop) against the ORACLE's taps, not just
-    against K1: depthwise outputs, SE gates and block outputs of blocks 2-6, and the final angles."""
-    import whenet_b200
-    crops = np.concatenate([sample_crops, jitter_crops])
-    m = whenet_b200.WHENet(SNAP, device=0, precision="bf16", max_batch=8)
-    m.set_option("k1_variant", 3)
-    m.set_option("k1p_min_crops", 1)
-    taps = {}
-    ref_ang = np.stack(oracle32.get_angle(crops, taps), axis=1)
-    m.enable_taps(True)
-    got = np.stack(m.get_angle(crops), axis=1)
-    for i in range(2, 7):
-        for kind in ("dw", "gate", "block"):
-            nm = "%s%d" % (kind, i)
-            ref = taps[nm].astype(np.float64).reshape(-1)
-            g = m.tap(nm).astype(np.float64)
-            e = float(np.sqrt(((g - ref) ** 2).mean()) / (np.sqrt((ref ** 2).mean()) + 1e-30))
-            assert e < 0.12, (nm, e)
-    assert np.abs(got - ref_ang).max() < 0.5
-    m.close()
-
-
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
 def test_k1w_taps_vs_oracle(prec, oracle32, sample_crops, jitter_crops):
     """K1W (k1_variant=4: weight-stationary persistent CTAs, TMA-staged input tiles, warp-specialised epilogue / depthwise):
