@@ -160,6 +160,8 @@ template <typename T, int KS, int S, int R, bool NOEXP = false, int CCT = 0, int
 __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(const K1Params p) {
     const int CC = CCT ? CCT : p.CC;
     const int pitchE = CCT ? CCT * 2 + 16 : p.pitchE;
+    // depthwise on HFMA2 (fp16 running sums over the fp16 E tile, fp16 weights): bf16 storage with an expand conv
+    constexpr bool HDW = !NOEXP && std::is_same<T, __nv_bfloat16>::value;
     constexpr int NG = NT / 128;                                // warp groups of four (one warp per TMEM lane quadrant)
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(con
         const int cbase = ch * CC;
         const uint32_t c_dst = sC + buf * p.smem_C;
         const int q = CC >> 2;                                   // 16-byte pieces per fp32 constant row
-        if (NOEXP) {
+        if (!HDW) {
             for (int idx = tid; idx < (KS * KS + 1) * q; idx += NT) {
                 const int row = div_small(idx, inv_q), j = idx - row * q;
                 const float* src = row == 0 ? p.b_dw + cbase + j * 4 : p.w_dw + (long long)(row - 1) * p.Cexp + cbase + j * 4;
@@ -405,7 +407,10 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(con
                 const int oyl = sidx >> p.spr_log2, oxl0 = (sidx - (oyl << p.spr_log2)) * R;
                 float2 acc[R][2];      // (ch0,ch1), (ch2,ch3): one FFMA2 (fma.rn.f32x2) per pair - same IEEE FMAs, half the issue slots
                 uint32_t erow = e_cv + (uint32_t)(oyl * S) * e_rowstride + (uint32_t)(oxl0 * S) * pitchE;
-                if constexpr (NOEXP) {
+                // fp16 storage mode keeps the fp32 FFMA2 form (E is fp16 there as well): that mode exists for its accuracy
+                // (0.02 deg), and fp16 running sums would double its error; bf16 storage gains accuracy AND speed from HFMA2
+                using TE = typename std::conditional<NOEXP, T, __half>::type;       // element type of the E tile
+                if constexpr (!HDW) {
 #pragma unroll
                     for (int r = 0; r < R; ++r) { acc[r][0] = make_float2(bq.x, bq.y); acc[r][1] = make_float2(bq.z, bq.w); }
 #pragma unroll
@@ -423,8 +428,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k1_expand_dw_kernel(con
                             lds64(ea, a, b);
                             ea += pitchE;
                             float2 x01, x23;
-                            unpack2<T>(a, x01.x, x01.y);
-                            unpack2<T>(b, x23.x, x23.y);
+                            unpack2<TE>(a, x01.x, x01.y);
+                            unpack2<TE>(b, x23.x, x23.y);
 #pragma unroll
                             for (int r = 0; r < R; ++r) {
                                 const int kx = col - r * S;          // compile-time after unrolling
