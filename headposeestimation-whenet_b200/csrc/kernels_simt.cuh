@@ -518,20 +518,25 @@ __device__ __forceinline__ void se_gate_fc(const float* mean, float* hid, const 
                                            int C, int Cse, float* gate_sm = nullptr) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    // The FMAs keep their sequential order (bitwise identical on every route); the weight LOADS of eight steps are issued
-    // together first - the serial chain of L2-latency loads was the whole cost of this kernel at C = 1152 (60 us / 512 crops).
+    // FC1: lane L owns the channels 128 k + 4 L + {0..3} (one 16-byte load per k; every load of a row is in flight at once -
+    // the serial chain of L2 round trips was the whole cost of the gate at C = 1152), FMAs in ascending channel order,
+    // then the xor-shuffle tree.  This order is the definition every route shares (se_gate_kernel, se_gate_batch_kernel,
+    // the tails of K1 / KD), so their gates agree bit for bit.
     for (int j = warp; j < Cse; j += NT / 32) {
         float s = 0.f;
         const float* wr = w1t + (long long)j * C;
-        int c = lane;
-        for (; c + 7 * 32 < C; c += 8 * 32) {
-            float wv[8];
+        for (int c0 = lane * 4; c0 < C; c0 += 8 * 128) {
+            float4 wv[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) wv[u] = wr[c + u * 32];
+            for (int u = 0; u < 8; ++u)
+                if (c0 + u * 128 < C) wv[u] = __ldg(reinterpret_cast<const float4*>(wr + c0 + u * 128));
 #pragma unroll
-            for (int u = 0; u < 8; ++u) s = fmaf(mean[c + u * 32], wv[u], s);
+            for (int u = 0; u < 8; ++u)
+                if (c0 + u * 128 < C) {
+                    const float4 mv = *reinterpret_cast<const float4*>(mean + c0 + u * 128);
+                    s = fmaf(mv.x, wv[u].x, s); s = fmaf(mv.y, wv[u].y, s); s = fmaf(mv.z, wv[u].z, s); s = fmaf(mv.w, wv[u].w, s);
+                }
         }
-        for (; c < C; c += 32) s = fmaf(mean[c], wr[c], s);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) hid[j] = swish_f(s + b1[j]);
@@ -591,6 +596,108 @@ __global__ void __launch_bounds__(NT) se_gate_kernel(const float* __restrict__ p
     extern __shared__ float sm[];   // mean[C] | hid[Cse]
     const int n = blockIdx.x;
     se_gate_crop<false, NT>(partial + (long long)n * tiles * C, tiles, inv_hw, w1t, b1, w2, b2, gate + (long long)n * C, C, Cse, sm);
+}
+
+// The same gates for SEB crops per CTA: the two FC matrices (2 x Cse x C floats - 442 KB at C = 1152) are read once per
+// SEB crops instead of once per crop, with 16-byte loads and every load of a row in flight together.  Every sum keeps the
+// order of se_gate_crop / se_gate_fc (partials: four chains by tile index; FC1: lane L owns channels 128 k + 4 L + i,
+// ascending, xor-shuffle tree; FC2: j ascending), so the gates are bit-identical to se_gate_kernel's and the routes can be
+// mixed freely.  Shared-memory arrays are 16-byte aligned: C % 4 == 0 (every block of the network).
+template <int SEB, int NT>
+__global__ void __launch_bounds__(NT) se_gate_batch_kernel(const float* __restrict__ partial, int tiles, float inv_hw,
+                                                            const float* __restrict__ w1t, const float* __restrict__ b1,
+                                                            const float* __restrict__ w2, const float* __restrict__ b2,
+                                                            float* __restrict__ gate, int C, int Cse, int N) {
+    extern __shared__ __align__(16) float sm[];   // mean[SEB][C] | hid[SEB][Cse]
+    float* mean = sm;
+    float* hid = sm + SEB * C;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * SEB;
+    const int nb = min(SEB, N - n0);
+    const int C4 = C >> 2;
+    for (int idx = tid; idx < SEB * C4; idx += NT) {
+        const int b = idx / C4, c = (idx - b * C4) * 4;
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < nb) {
+            const float* q0 = partial + (long long)(n0 + b) * tiles * C + c;
+            float4 s0 = m, s1 = m, s2 = m, s3 = m;
+            auto add = [](float4& a, const float4 v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; };
+            int t = 0;
+            for (; t + 3 < tiles; t += 4) {
+                const float* q = q0 + (long long)t * C;
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(q)), v1 = __ldg(reinterpret_cast<const float4*>(q + C));
+                const float4 v2 = __ldg(reinterpret_cast<const float4*>(q + 2 * C)), v3 = __ldg(reinterpret_cast<const float4*>(q + 3 * C));
+                add(s0, v0); add(s1, v1); add(s2, v2); add(s3, v3);
+            }
+            for (; t < tiles; ++t) add(s0, __ldg(reinterpret_cast<const float4*>(q0 + (long long)t * C)));
+            m.x = ((s0.x + s1.x) + (s2.x + s3.x)) * inv_hw; m.y = ((s0.y + s1.y) + (s2.y + s3.y)) * inv_hw;
+            m.z = ((s0.z + s1.z) + (s2.z + s3.z)) * inv_hw; m.w = ((s0.w + s1.w) + (s2.w + s3.w)) * inv_hw;
+        }
+        *reinterpret_cast<float4*>(mean + b * C + c) = m;
+    }
+    __syncthreads();
+    for (int j = warp; j < Cse; j += NT / 32) {
+        float s[SEB];
+#pragma unroll
+        for (int b = 0; b < SEB; ++b) s[b] = 0.f;
+        const float* wr = w1t + (long long)j * C;
+        for (int c0 = lane * 4; c0 < C; c0 += 8 * 128) {
+            float4 wv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (c0 + u * 128 < C) wv[u] = __ldg(reinterpret_cast<const float4*>(wr + c0 + u * 128));
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (c0 + u * 128 < C) {
+#pragma unroll
+                    for (int b = 0; b < SEB; ++b) {
+                        const float4 mv = *reinterpret_cast<const float4*>(mean + b * C + c0 + u * 128);
+                        s[b] = fmaf(mv.x, wv[u].x, s[b]); s[b] = fmaf(mv.y, wv[u].y, s[b]);
+                        s[b] = fmaf(mv.z, wv[u].z, s[b]); s[b] = fmaf(mv.w, wv[u].w, s[b]);
+                    }
+                }
+        }
+#pragma unroll
+        for (int b = 0; b < SEB; ++b) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s[b] += __shfl_xor_sync(0xffffffffu, s[b], o);
+        }
+        if (lane == 0) {
+            const float bj = b1[j];
+#pragma unroll
+            for (int b = 0; b < SEB; ++b) hid[b * Cse + j] = swish_f(s[b] + bj);
+        }
+    }
+    __syncthreads();
+    // FC2: one thread per four channels, sixteen weight rows in flight per step
+    for (int c = tid * 4; c < C; c += NT * 4) {
+        float4 s[SEB];
+        const float4 bc = __ldg(reinterpret_cast<const float4*>(b2 + c));
+#pragma unroll
+        for (int b = 0; b < SEB; ++b) s[b] = bc;
+        const float* wc = w2 + c;
+        for (int j0 = 0; j0 < Cse; j0 += 16) {
+            float4 wv[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u)
+                if (j0 + u < Cse) wv[u] = __ldg(reinterpret_cast<const float4*>(wc + (long long)(j0 + u) * C));
+#pragma unroll
+            for (int u = 0; u < 16; ++u)
+                if (j0 + u < Cse) {
+#pragma unroll
+                    for (int b = 0; b < SEB; ++b) {
+                        const float h = hid[b * Cse + j0 + u];
+                        s[b].x = fmaf(h, wv[u].x, s[b].x); s[b].y = fmaf(h, wv[u].y, s[b].y);
+                        s[b].z = fmaf(h, wv[u].z, s[b].z); s[b].w = fmaf(h, wv[u].w, s[b].w);
+                    }
+                }
+        }
+#pragma unroll
+        for (int b = 0; b < SEB; ++b)
+            if (b < nb)
+                *reinterpret_cast<float4*>(gate + (long long)(n0 + b) * C + c) =
+                    make_float4(sigmoid_f(s[b].x), sigmoid_f(s[b].y), sigmoid_f(s[b].z), sigmoid_f(s[b].w));
+    }
 }
 
 // softmax (reference utils.py:7-11: exp(x - max) / sum) and the bin-index expectation (reference whenet.py:31-33) of the

@@ -174,7 +174,8 @@ template <> __device__ __forceinline__ uint4 scale8s<__half>(uint4 raw, uint32_t
     return raw;
 }
 
-template <typename T, bool SWISH, int GATE, bool RESID>
+// OUT_H: the result is written as fp16 whatever T is (the expand conv feeding the HFMA2 depthwise kernel KD)
+template <typename T, bool SWISH, int GATE, bool RESID, bool OUT_H = false>
 __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, const T* __restrict__ Wt,
                                                      const float* __restrict__ bias, const float* __restrict__ gate,
                                                      const T* __restrict__ resid, T* __restrict__ out,
@@ -393,7 +394,8 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
 #pragma unroll
                     for (int j = 0; j < 8; ++j) o[j] += r[j];
                 }
-                st8<T>(reinterpret_cast<T*>(stage + tid * pitch16 + ((c0 >> 3) + h)), o);
+                if (OUT_H) st8<__half>(reinterpret_cast<__half*>(stage + tid * pitch16 + ((c0 >> 3) + h)), o);
+                else st8<T>(reinterpret_cast<T*>(stage + tid * pitch16 + ((c0 >> 3) + h)), o);
             }
         }
     }
@@ -412,7 +414,8 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
 
 template <typename T>
 int launch_pw_tc2(cudaStream_t stream, int* tflag, const T* A, const void* Wt16, const float* bias, const float* gate, const T* resid,
-                  T* out, long long M, int K, int N, int hw, bool swish, int stage_cap = 0, int smem_budget_kb = 54, int min_ctas = 296) {
+                  T* out, long long M, int K, int N, int hw, bool swish, int stage_cap = 0, int smem_budget_kb = 54, int min_ctas = 296,
+                  bool out_half = false) {
     if (sizeof(T) != 2) return 1;
     if ((K & 7) || (N & 7) || M > 0x7fffffffLL) return 1;
     const bool per_crop = gate && hw >= 784;                 // gate on W, tiles stay inside a crop
@@ -454,17 +457,18 @@ int launch_pw_tc2(cudaStream_t stream, int* tflag, const T* A, const void* Wt16,
     if (smem > 225 * 1024) return 1;
     dim3 grid((unsigned)((N + n_tile - 1) / n_tile), (unsigned)m_tiles);
     const T* W = reinterpret_cast<const T*>(Wt16);
-#define TC2(SW, GA, RE)                                                                                              \
+#define TC2(SW, GA, RE, OH)                                                                                          \
     do {                                                                                                             \
-        auto kfn = pw_tc2_kernel<T, SW, GA, RE>;                                                                     \
+        auto kfn = pw_tc2_kernel<T, SW, GA, RE, OH>;                                                       \
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024) != cudaSuccess) return -1; \
         kfn<<<grid, 128, smem, stream>>>(A, W, bias, gate, resid, out, (int)M, K, N, hw, n_tile, umma_n, tmem_cols, n_stages, tpc, idesc, tflag); \
     } while (0)
-    if (swish && !gate && !resid) TC2(true, 0, false);
-    else if (!swish && !gate && !resid) TC2(false, 0, false);
-    else if (!swish && !gate && resid) TC2(false, 0, true);           // project conv whose input K1 has already gated
-    else if (!swish && gate && !resid) { if (per_crop) TC2(false, 2, false); else TC2(false, 1, false); }
-    else if (!swish && gate && resid) { if (per_crop) TC2(false, 2, true); else TC2(false, 1, true); }
+    if (out_half && !(swish && !gate && !resid)) return 1;
+    if (swish && !gate && !resid) { if (out_half) TC2(true, 0, false, true); else TC2(true, 0, false, false); }
+    else if (!swish && !gate && !resid) TC2(false, 0, false, false);
+    else if (!swish && !gate && resid) TC2(false, 0, true, false);           // project conv whose input K1 has already gated
+    else if (!swish && gate && !resid) { if (per_crop) TC2(false, 2, false, false); else TC2(false, 1, false, false); }
+    else if (!swish && gate && resid) { if (per_crop) TC2(false, 2, true, false); else TC2(false, 1, true, false); }
     else return 1;
 #undef TC2
     return 0;

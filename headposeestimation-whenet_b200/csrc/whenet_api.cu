@@ -23,6 +23,7 @@
 #include "kernels_k1w.cuh"
 #include "kernels_k2.cuh"
 #include "kernels_tc32.cuh"
+#include "kernels_dwse.cuh"
 #include <cudaTypedefs.h>
 
 // The fused-kernel launchers are instantiated in their own translation units (inst_k1_bf16.cu, inst_k1_f16.cu, inst_k1x.cu)
@@ -35,7 +36,17 @@ namespace fused {
 WHENET_EXTERN_FUSED(__nv_bfloat16)
 WHENET_EXTERN_FUSED(__half)
 #undef WHENET_EXTERN_FUSED
+extern template int launch_dwse<__nv_bfloat16>(cudaStream_t, DwSeParams, int, int, int, int, int);
 }  // namespace fused
+namespace tc {
+#define WHENET_EXTERN_PW(T)                                                                                                         \
+    extern template int launch_pw_tc2<T>(cudaStream_t, int*, const T*, const void*, const float*, const float*, const T*, T*, long long, \
+                                         int, int, int, bool, int, int, int, bool);                                                 \
+    extern template int launch_k2<T>(cudaStream_t, const K2Params&, size_t, bool, bool, bool, int, bool);
+WHENET_EXTERN_PW(__nv_bfloat16)
+WHENET_EXTERN_PW(__half)
+#undef WHENET_EXTERN_PW
+}  // namespace tc
 }  // namespace whenet
 
 namespace {
@@ -133,7 +144,8 @@ struct whenet_ctx {
     int* h_tflag = nullptr; // mbarrier-timeout flag: mapped pinned host memory, raised by any tcgen05 kernel of this context
     int* d_tflag = nullptr; // ... its device address (kernel parameter)
     int dw_variant = 1;     // 0 = one output per thread, 1 = register-blocked strips
-    int pw_variant = 2;     // tensor-core 1x1 kernel: 2 = pw_tc2 (one tile per CTA, cp.async ring), 3 = K2 (persistent, TMA, warp-specialised)
+    int pw_variant = 4;     // tensor-core 1x1 kernel: 2 = pw_tc2 (one tile per CTA, cp.async ring), 3 = K2 (persistent, TMA, warp-specialised),
+                            // 4 = per layer (launch_pw)
     std::map<TmapKey, CUtensorMap> tmaps2;  // K2 tensor maps: activations by (K, M, pointer), weights by (-N, K, pointer)
     int pw_stage_cap = 0, pw_smem_kb = 54, pw_min_ctas = 148;    // pw_tc2 ring: max stages (0 = up to 4) and per-CTA smem budget that trades depth for co-residency
     int stem_variant = 1;   // 0 = 4 threads / pixel straight from global, 1 = smem-tiled, weights in the constant bank
@@ -149,6 +161,10 @@ struct whenet_ctx {
     std::vector<GraphEntry> graphs;
     int use_fused = 0;      // K1: expand + depthwise in one kernel (16-bit storage only; default on for bf16/fp16)
     int fused_max_block = 16;  // blocks 2..fused_max_block use K1
+    int kd_expand_k2 = 1;      // the expand GEMM of the KD route: 1 = persistent K2 kernel, 0 = pw_tc2
+    int kd_tail = 0;           // KD computes the SE gate and gates its output itself (1) or leaves both to se_gate + the project conv (0)
+    int se_batch = 1;          // batches >= 64: se_gate_batch_kernel (four crops per CTA)
+    int kd_from = 7;           // bf16: blocks >= kd_from whose map fits one CTA run expand GEMM (fp16 E through L2) + KD; 0 = off
     std::vector<K1Plan> k1;
     std::vector<K1WPlan> k1w;  // k1_variant 4: weight-stationary persistent K1 (TMA-staged input tiles)
     std::map<TmapKey, CUtensorMap> tmaps;   // input tensor maps of K1W by (block, crops, buffer)
@@ -379,15 +395,20 @@ int make_tmap_w(CUtensorMap* tm, const void* base, int rows, int K, int box_rows
 // ----------------------------------------------------------------------------- launches
 template <typename T>
 int launch_pw(whenet_ctx* c, const char* name, const T* A, const float* W, const void* Wt16, const float* bias,
-              const float* gate, const T* resid, T* out, long long M, int K, int N, int hw, bool swish) {
+              const float* gate, const T* resid, T* out, long long M, int K, int N, int hw, bool swish, bool out_half = false) {
     const double bytes = (double)M * (K + N + (resid ? N : 0)) * sizeof(T);
     const double flops = 2.0 * (double)M * K * N;
     Scope sc(c, name, bytes, flops);
     if constexpr (sizeof(T) == 2) {
-        if (c->use_tc && Wt16 && c->pw_variant == 3) {
+        // pw_variant 4 (default): K2 for the ungated convs (expands, head, projects whose input is already gated) and for the gated
+        // projects of the small maps; pw_tc2 (per-crop gate on W) for the gated projects of blocks 1-6
+        const bool want_k2 = c->pw_variant == 3 || (c->pw_variant == 4 && (gate == nullptr || hw <= 196) && (!out_half || c->kd_expand_k2));
+        if (c->use_tc && Wt16 && want_k2) {
             whenet::tc::K2Params kp{};
             size_t smem = 0;
-            if (whenet::tc::plan_k2(M, K, N, hw, gate != nullptr, c->precision == WHENET_PRECISION_BF16, &kp, &smem)) {
+            // (the persistent kernel needs enough tiles to keep every SM busy for a while; below that pw_tc2's N split wins)
+            if (whenet::tc::plan_k2(M, K, N, hw, gate != nullptr, c->precision == WHENET_PRECISION_BF16, &kp, &smem) &&
+                (c->pw_variant == 3 || kp.tiles >= 2 * c->sm_count)) {
                 if (c->tmaps2.size() > 1024) c->tmaps2.clear();
                 const TmapKey ka{K, (int)M, (const void*)A}, kw{-N, K, Wt16};
                 auto ia = c->tmaps2.find(ka);
@@ -406,14 +427,14 @@ int launch_pw(whenet_ctx* c, const char* name, const T* A, const float* W, const
                 }
                 kp.tmA = ia->second; kp.tmW = iw->second;
                 kp.bias = bias; kp.gate = gate; kp.resid = resid; kp.out = out; kp.tflag = c->d_tflag;
-                int rc = whenet::tc::launch_k2<T>(c->stream, kp, smem, swish, gate != nullptr, resid != nullptr, c->sm_count);
+                int rc = whenet::tc::launch_k2<T>(c->stream, kp, smem, swish, gate != nullptr, resid != nullptr, c->sm_count, out_half);
                 if (rc == 0) { CK(cudaGetLastError()); return 0; }
                 if (rc < 0) return fail(WHENET_ECUDA, "K2 launch failed for %s (rc=%d)", name, rc);
             }
             // shape or epilogue not covered by K2 -> pw_tc2 below
         }
         if (c->use_tc && Wt16) {
-            int rc = whenet::tc::launch_pw_tc2<T>(c->stream, c->d_tflag, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish, c->pw_stage_cap, c->pw_smem_kb, c->pw_min_ctas);
+            int rc = whenet::tc::launch_pw_tc2<T>(c->stream, c->d_tflag, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish, c->pw_stage_cap, c->pw_smem_kb, c->pw_min_ctas, out_half);
             if (rc == 0) { CK(cudaGetLastError()); return 0; }
             if (rc < 0) return fail(WHENET_ECUDA, "tensor-core 1x1 launch failed for %s (rc=%d)", name, rc);
             // rc > 0: shape not supported by the tensor-core kernel -> CUDA-core kernel below
@@ -426,6 +447,7 @@ int launch_pw(whenet_ctx* c, const char* name, const T* A, const float* W, const
             if (rc < 0) return fail(WHENET_ECUDA, "split-bf16 tensor-core 1x1 launch failed for %s (rc=%d)", name, rc);
         }
     }
+    if (out_half) return fail(WHENET_EINVAL, "fp16-output 1x1 conv needs the tensor-core kernel (%s)", name);
     dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
 #define PW(SW, GA, RE) whenet::pw_conv_kernel<T, SW, GA, RE><<<grid, 256, 0, c->stream>>>(A, W, bias, gate, resid, out, M, K, N, hw)
     if (swish && !gate && !resid) PW(true, false, false);
@@ -500,6 +522,9 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
         bool did_k1 = false;
         bool se_in_k1 = false;      // the SE gate came out of the fused kernel's tail (options se_fused / se_tail)
         bool d_gated = false;       // ... and D already carries it
+        // bf16 late blocks (whole map in one CTA): expand GEMM + KD instead of K1
+        const bool use_kd = std::is_same<T, __nv_bfloat16>::value && c->use_fused && c->use_tc && c->kd_from > 0 && b.idx >= c->kd_from &&
+                            b.has_expand && whenet::fused::dwse_chunk(b.k, b.s, b.hin, b.cexp) > 0;
         if constexpr (sizeof(T) == 2) {
             if (i == 0 && !did_k1 && c->use_fused && c->dw1_fused && c->dw1.valid) {
                 whenet::fused::K1Params p = c->dw1.p;
@@ -514,6 +539,39 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
                 CK(cudaGetLastError());
                 tiles = p.tiles_x * p.tiles_y;
                 did_k1 = true;
+            } else if (use_kd) {
+              if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                // late blocks: expand as a plain tcgen05 GEMM (fp16 E, L2-resident) + KD (depthwise + SE + gating)
+                snprintf(nm, sizeof nm, "b%02d.expand", b.idx);
+                int rc = launch_pw<T>(c, nm, cur, w.w_exp, w.wt_exp, w.b_exp, nullptr, nullptr, E,
+                                      (long long)nb * b.hin * b.hin, b.cin, b.cexp, b.hin * b.hin, true, true);
+                if (rc) return rc;
+                whenet::fused::DwSeParams p{};
+                p.E = reinterpret_cast<const __half*>(E); p.w16 = reinterpret_cast<const __half*>(w.w_dw16); p.b_dw = w.b_dw_h;
+                p.out = D; p.partial = c->d_partial;
+                p.w_se1t = w.w_se1t; p.b_se1 = w.b_se1; p.w_se2 = w.w_se2; p.b_se2 = w.b_se2; p.gate = c->d_gate; p.Cse = b.cse;
+                p.inv_hw = 1.0f / (float)(b.hout * b.hout);
+                p.C = b.cexp; p.pad = b.pad;
+                // small batches: spread one crop's channel chunks over several CTAs (the gate then comes from se_gate_kernel)
+                int split = 1;
+                {
+                    const int n_chunks = b.cexp / whenet::fused::dwse_chunk(b.k, b.s, b.hin, b.cexp);
+                    while (split < n_chunks && (long long)nb * split < c->k1_split_ctas) ++split;
+                }
+                if (split == 1 && c->se_tail && c->kd_tail) {
+                    p.se_tail = 1;
+                    se_in_k1 = true;
+                    if (c->se_scale_out && !taps) { p.scale_out = 1; d_gated = true; }
+                }
+                snprintf(nm, sizeof nm, "b%02d.kd", b.idx);
+                Scope sc(c, nm, (double)nb * ((double)b.hin * b.hin + (double)b.hout * b.hout) * b.cexp * sizeof(T),
+                         2.0 * nb * (double)b.hout * b.hout * b.k * b.k * b.cexp);
+                rc = whenet::fused::launch_dwse<T>(c->stream, p, b.k, b.s, b.hin, nb, split);
+                if (rc != 0) return fail(WHENET_ECUDA, "KD launch failed for block %d (rc=%d)", b.idx, rc);
+                CK(cudaGetLastError());
+                tiles = 1;
+                did_k1 = true;
+              }
             } else if (c->use_fused && c->k1_variant == 4 && c->k1w[i].valid && b.idx <= c->fused_max_block) {
                 const K1WPlan& pl = c->k1w[i];
                 whenet::fused::K1WParams p = pl.p;
@@ -592,7 +650,12 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
             Scope sc(c, nm, (double)nb * (tiles + 1) * b.cexp * 4.0, 4.0 * nb * b.cexp * b.cse);
             const float inv_hw = 1.0f / (float)(b.hout * b.hout);
             const size_t se_smem = (b.cexp + b.cse) * sizeof(float);
-            if (nb < 64 || c->se_wide)     // 32 warps per crop cut the FC latency chain
+            if (nb >= 64 && c->se_batch) {
+                // throughput batches: four crops per CTA share every FC weight load (bit-identical gates)
+                constexpr int SEB = 4;
+                whenet::se_gate_batch_kernel<SEB, 256><<<(nb + SEB - 1) / SEB, 256, SEB * se_smem, c->stream>>>(
+                    c->d_partial, tiles, inv_hw, w.w_se1t, w.b_se1, w.w_se2, w.b_se2, c->d_gate, b.cexp, b.cse, nb);
+            } else if (nb < 64 || c->se_wide)     // 32 warps per crop cut the FC latency chain
                 whenet::se_gate_kernel<1024><<<nb, 1024, se_smem, c->stream>>>(
                     c->d_partial, tiles, inv_hw, w.w_se1t, w.b_se1, w.w_se2, w.b_se2, c->d_gate, b.cexp, b.cse);
             else
@@ -1481,6 +1544,10 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!strcmp(key, "pw_min_ctas")) { c->pw_min_ctas = value; return 0; }
     if (!strcmp(key, "fused")) { c->use_fused = value && c->precision != WHENET_PRECISION_FP32; return 0; }
     if (!strcmp(key, "fused_max_block")) { c->fused_max_block = value; return 0; }
+    if (!strcmp(key, "kd_from")) { c->kd_from = value; return 0; }
+    if (!strcmp(key, "kd_expand_k2")) { c->kd_expand_k2 = value; return 0; }
+    if (!strcmp(key, "kd_tail")) { c->kd_tail = value; return 0; }
+    if (!strcmp(key, "se_batch")) { c->se_batch = value; return 0; }
     if (!strcmp(key, "chunk")) {
         if (value < 1) return fail(WHENET_EINVAL, "chunk must be >= 1");
         c->chunk = std::min(value, c->max_batch);

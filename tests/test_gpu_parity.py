@@ -133,6 +133,7 @@ def test_fused_k1_taps(prec, oracle32, sample_crops):
     m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=8)
     m.set_option("fused", 1)
     m.set_option("fused_max_block", 16)
+    m.set_option("kd_from", 0)               # K1 on the late blocks too (the default bf16 route there is KD: test_kd_route)
     taps = {}
     oracle32.get_angle(sample_crops, taps)
     m.enable_taps(True)
@@ -172,6 +173,7 @@ def test_fused_k1_plan_variants(prec, plan_set, oracle32, sample_crops, jitter_c
     import whenet_b200
     crops = np.concatenate([sample_crops, jitter_crops[:1]])
     m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=8)
+    m.set_option("kd_from", 0)
     for blk, plan in K1_PLAN_SETS[plan_set].items():
         assert m.set_k1_plan(blk, *plan), (blk, plan)
     taps = {}
@@ -196,6 +198,74 @@ def test_fused_k1_plan_variants(prec, plan_set, oracle32, sample_crops, jitter_c
     m.close()
 
 
+def test_kd_route(oracle32, sample_crops, jitter_crops):
+    """Late blocks (7-16) in bf16: expand as a tcgen05 GEMM writing fp16 E + KD (depthwise + squeeze-excite + gating in one
+    kernel, kernels_dwse.cuh).  Depthwise outputs, gates and block outputs against the oracle; agreement with the K1 route
+    (same arithmetic up to the rounding of the expand accumulators); bitwise equality of the chunk-split route (small
+    batches: several CTAs per crop, gate from se_gate_kernel, gated project conv) and the one-CTA-per-crop route (gate and
+    gating in the kernel tail); bitwise batch invariance."""
+    import whenet_b200
+    crops = np.concatenate([sample_crops, jitter_crops[:3]])
+    m = whenet_b200.WHENet(SNAP, device=0, precision="bf16", max_batch=8)
+    m.set_option("kd_from", 0)
+    launches0 = m.launch_count()
+    k1 = np.stack(m.get_angle(crops), axis=1)
+    n_k1 = m.launch_count() - launches0
+    m.set_option("kd_from", 7)
+    launches0 = m.launch_count()
+    split = np.stack(m.get_angle(crops), axis=1)          # 5 crops: chunks split over CTAs
+    n_kd = m.launch_count() - launches0
+    assert n_kd == n_k1 + 10                               # expand + KD instead of K1 on ten blocks
+    assert np.abs(split - k1).max() < 0.25
+    m.set_option("k1_split_ctas", 0)                       # one CTA per crop, gate still from se_gate + gated project (the default)
+    assert np.array_equal(np.stack(m.get_angle(crops), axis=1), split)
+    m.set_option("kd_tail", 1)                             # ... SE tail (+ in-place gating) inside KD
+    for so in (0, 1):
+        m.set_option("se_scale_out", so)
+        tail = np.stack(m.get_angle(crops), axis=1)
+        assert np.array_equal(tail, split), so
+    m.set_option("kd_tail", 0)
+    for i in (0, 4):
+        one = np.stack(m.get_angle(crops[i:i + 1]), axis=1)
+        assert np.array_equal(one[0], split[i])
+    taps = {}
+    ref_ang = np.stack(oracle32.get_angle(crops, taps), axis=1)
+    m.enable_taps(True)
+    got = np.stack(m.get_angle(crops), axis=1)
+    for i in range(1, 17):
+        for kind in ("dw", "gate", "block"):
+            nm = "%s%d" % (kind, i)
+            r = taps[nm].astype(np.float64).reshape(-1)
+            g = m.tap(nm).astype(np.float64)
+            e = float(np.sqrt(((g - r) ** 2).mean()) / (np.sqrt((r ** 2).mean()) + 1e-30))
+            assert e < 0.12, (nm, e)
+    assert np.abs(got - ref_ang).max() < 0.6
+    m.close()
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_se_batch_and_k2_routes_bitwise(prec, sample_crops, jitter_crops):
+    """Throughput-sized batches switch two kernels: the SE gates come from se_gate_batch_kernel (four crops per CTA share
+    the FC weight loads) and the ungated / small-map 1x1 convs run on the persistent K2 kernel.  Both must give the bits of
+    the small-batch routes (se_gate_kernel, pw_tc2)."""
+    import whenet_b200
+    crops = np.concatenate([sample_crops, jitter_crops] * 9)[:70]
+    m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=128)
+    m.set_option("streams", 1)
+    ref = np.stack(m.get_angle(crops), axis=1)
+    small = np.concatenate([np.stack(m.get_angle(crops[i:i + 8]), axis=1) for i in range(0, 70, 8)])
+    assert np.array_equal(ref, small)
+    m.set_option("se_batch", 0)
+    assert np.array_equal(np.stack(m.get_angle(crops), axis=1), ref)
+    m.set_option("se_batch", 1)
+    m.set_option("pw_variant", 2)                          # pw_tc2 everywhere
+    assert np.array_equal(np.stack(m.get_angle(crops), axis=1), ref)
+    m.set_option("pw_variant", 3)                          # K2 everywhere: the gated projects of blocks 1-6 then scale A rows
+    all_k2 = np.stack(m.get_angle(crops), axis=1)          # (bf16(a*g)) instead of W rows (bf16(w*g)) - same maths, other rounding
+    assert np.abs(all_k2 - ref).max() < (0.5 if prec == "bf16" else 0.05)
+    m.close()
+
+
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
 def test_se_tail_paths_bitwise(prec, oracle32, sample_crops, jitter_crops):
     """Blocks whose K1 CTA holds whole crops compute the SE gate in the kernel tail and gate their depthwise output in
@@ -204,6 +274,7 @@ def test_se_tail_paths_bitwise(prec, oracle32, sample_crops, jitter_crops):
     import whenet_b200
     crops = np.concatenate([sample_crops, jitter_crops[:3]])          # 5 crops: the last two-crop CTA is half empty
     m = whenet_b200.WHENet(SNAP, device=0, precision=prec, max_batch=8)
+    m.set_option("kd_from", 0)                 # K1 on the late blocks (the KD route has its own test)
     m.set_option("se_tail", 0)
     ref = np.stack(m.get_angle(crops), axis=1)
     m.set_option("se_tail", 1)
@@ -236,12 +307,14 @@ def test_se_tail_paths_bitwise(prec, oracle32, sample_crops, jitter_crops):
     m.close()
 
 
-def test_fused_k1_batch_invariance(sample_crops, jitter_crops):
+@pytest.mark.parametrize("kd_from", [0, 7])
+def test_fused_k1_batch_invariance(kd_from, sample_crops, jitter_crops):
     import whenet_b200
     crops = np.concatenate([sample_crops, jitter_crops] * 3)[:19]
     m = whenet_b200.WHENet(SNAP, device=0, precision="bf16", max_batch=32)
     m.set_option("fused", 1)
     m.set_option("fused_max_block", 16)
+    m.set_option("kd_from", kd_from)
     full = np.stack(m.get_angle(crops), axis=1)
     for i in (0, 7, 18):
         one = np.stack(m.get_angle(crops[i:i + 1]), axis=1)

@@ -26,14 +26,15 @@ for prec in os.environ.get("PRECS", "fp32,bf16,fp16").split(","):
             r = taps[nm].reshape(-1).astype(np.float64); g = m.tap(nm).astype(np.float64)
             print("   %-8s rel-max %.3e rel-rms %.3e" % (nm, np.abs(g - r).max() / np.abs(r).max(), np.sqrt(((g - r) ** 2).mean() / (r ** 2).mean())))
         rng = np.random.default_rng(0)
-        for n in (32, 512):
+        NP = int(os.environ.get("NPROF", "512"))
+        for n in (32, NP):
             x = rng.integers(0, 256, (n, 224, 224, 3), dtype=np.uint8)
             m.get_angle(x)
             t = time.time(); m.get_angle(x); dt = time.time() - t
             print("   N=%d host-e2e %.2f ms -> %.0f crops/s" % (n, dt * 1e3, n / dt))
         m.enable_profile(True); m.get_angle(x); st = m.read_profile(); m.enable_profile(False)
         tot = sum(s["ms"] for s in st)
-        print("   profile N=512 total kernel ms %.3f -> %.0f crops/s device" % (tot, 512 / tot * 1e3))
+        print("   profile N=%d total kernel ms %.3f -> %.0f crops/s device" % (NP, tot, NP / tot * 1e3))
         for s in (st if os.environ.get("FULL") else sorted(st, key=lambda s: -s["ms"])[:12]):
             print("     %-16s %.3f ms  %.1f GB/s  %.2f TFLOP/s" % (s["name"], s["ms"], s["bytes"] / s["ms"] / 1e6, s["flops"] / s["ms"] / 1e9))
         m.close()
