@@ -324,6 +324,7 @@ def main():
             nm = s["name"]
             f = "pw_conv(1x1)" if (nm.endswith(".expand") or nm.endswith(".project") or nm == "head.conv") else \
                 "k1_expand_dw(fused)" if nm.endswith(".k1") else \
+                "kd_dw_se(late blocks)" if nm.endswith(".kd") else \
                 "dw_conv" if nm.endswith(".dw") else "se_gate" if nm.endswith(".se") else nm
             a = fam.setdefault(f, {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "launches": 0})
             for k in ("ms", "bytes", "flops", "launches"):

@@ -653,7 +653,7 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
             if (nb >= 64 && c->se_batch) {
                 // throughput batches: four crops per CTA share every FC weight load (bit-identical gates)
                 constexpr int SEB = 4;
-                whenet::se_gate_batch_kernel<SEB, 256><<<(nb + SEB - 1) / SEB, 256, SEB * se_smem, c->stream>>>(
+                whenet::se_gate_batch_kernel<SEB, 512><<<(nb + SEB - 1) / SEB, 512, SEB * se_smem, c->stream>>>(
                     c->d_partial, tiles, inv_hw, w.w_se1t, w.b_se1, w.w_se2, w.b_se2, c->d_gate, b.cexp, b.cse, nb);
             } else if (nb < 64 || c->se_wide)     // 32 warps per crop cut the FC latency chain
                 whenet::se_gate_kernel<1024><<<nb, 1024, se_smem, c->stream>>>(
