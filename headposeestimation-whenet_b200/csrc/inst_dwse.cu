@@ -4,5 +4,6 @@
 namespace whenet {
 namespace fused {
 template int launch_dwse<__nv_bfloat16>(cudaStream_t, DwSeParams, int, int, int, int, int);
+template int launch_dwse_spatial<__nv_bfloat16>(cudaStream_t, DwSeParams, int, int, int);
 }  // namespace fused
 }  // namespace whenet

@@ -37,6 +37,7 @@ WHENET_EXTERN_FUSED(__nv_bfloat16)
 WHENET_EXTERN_FUSED(__half)
 #undef WHENET_EXTERN_FUSED
 extern template int launch_dwse<__nv_bfloat16>(cudaStream_t, DwSeParams, int, int, int, int, int);
+extern template int launch_dwse_spatial<__nv_bfloat16>(cudaStream_t, DwSeParams, int, int, int);
 }  // namespace fused
 namespace tc {
 #define WHENET_EXTERN_PW(T)                                                                                                         \
@@ -164,6 +165,8 @@ struct whenet_ctx {
     int kd_expand_k2 = 1;      // the expand GEMM of the KD route: 1 = persistent K2 kernel, 0 = pw_tc2
     int kd_tail = 0;           // KD computes the SE gate and gates its output itself (1) or leaves both to se_gate + the project conv (0)
     int se_batch = 1;          // batches >= 64: se_gate_batch_kernel (four crops per CTA)
+    int dw1_kd = 1;            // bf16: the stem writes fp16 and block 1's depthwise runs on KD (spatial tiles, TMA, HFMA2) instead of K1's depthwise half
+    int head_batch = 1;        // batches >= 64: GAP kernel + Dense/decode for four crops per CTA
     int kd_from = 7;           // bf16: blocks >= kd_from whose map fits one CTA run expand GEMM (fp16 E through L2) + KD; 0 = off
     std::vector<K1Plan> k1;
     std::vector<K1WPlan> k1w;  // k1_variant 4: weight-stationary persistent K1 (TMA-staged input tiles)
@@ -392,6 +395,33 @@ int make_tmap_w(CUtensorMap* tm, const void* base, int rows, int K, int box_rows
     return 0;
 }
 
+// KD operands (fp16, no swizzle): E [n][H][H][C] with box {cc, pw, pw, 1} (started at (-pad, -pad) the out-of-image part of the
+// box is zero-filled = TF-SAME padding), depthwise weights [kk][C] with box {cc, kk}
+int make_tmap_kd_e(CUtensorMap* tm, const void* base, int n, int H, int C, int cc, int pw) {
+    auto fn = tmap_encode_fn();
+    if (!fn) return fail(WHENET_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)H, (cuuint64_t)n};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)H * C * 2, (cuuint64_t)H * H * C * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)cc, (cuuint32_t)pw, (cuuint32_t)pw, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(WHENET_ECUDA, "cuTensorMapEncodeTiled(KD tile %dx%dx%dx%d, box %dx%dx%d) failed: %d", n, H, H, C, pw, pw, cc, (int)r);
+    return 0;
+}
+int make_tmap_kd_w(CUtensorMap* tm, const void* base, int kk, int C, int cc) {
+    auto fn = tmap_encode_fn();
+    if (!fn) return fail(WHENET_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)kk};
+    const cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)cc, (cuuint32_t)kk};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(WHENET_ECUDA, "cuTensorMapEncodeTiled(KD weights %dx%d, box %d) failed: %d", kk, C, cc, (int)r);
+    return 0;
+}
+
 // ----------------------------------------------------------------------------- launches
 template <typename T>
 int launch_pw(whenet_ctx* c, const char* name, const T* A, const float* W, const void* Wt16, const float* bias,
@@ -502,10 +532,15 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
     T* oth = (T*)c->bufB;
     T* E = (T*)c->bufE;
     T* D = (T*)c->bufD;
+    const bool stem_half = std::is_same<T, __nv_bfloat16>::value && c->use_fused && c->use_tc && c->dw1_kd && c->stem_variant != 0 && !c->blocks.empty() &&
+                           !c->blocks[0].has_expand && c->blocks[0].cexp == 32 && c->blocks[0].k == 3 && c->blocks[0].s == 1 && c->blocks[0].hin % 14 == 0;
     {
         Scope sc(c, "stem", (double)nb * (kImgElems * (IN_U8 ? 1.0 : 4.0) + 112.0 * 112 * 32 * sizeof(T)),
                  2.0 * nb * 112.0 * 112 * 27 * 32);
-        if (c->stem_variant == 0) {
+        if (stem_half) {
+            // block 1's depthwise is KD (HFMA2 over an fp16 tile): the stem output, read by nothing else, is written as fp16
+            whenet::stem_tile_kernel<__half, IN_U8, true><<<dim3(56, nb), 224, 0, c->stream>>>(d_in, reinterpret_cast<__half*>(cur), c->stem_params, c->lut);
+        } else if (c->stem_variant == 0) {
             const long long total = (long long)nb * 112 * 112 * 4;
             whenet::stem_kernel<T, IN_U8><<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_in, cur, c->w_stem, c->b_stem, c->lut, nb);
         } else {
@@ -513,7 +548,11 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
         }
         CK(cudaGetLastError());
     }
-    if (taps) { int rc = add_tap<T>(c, "stem", cur, (size_t)nb * 112 * 112 * 32); if (rc) return rc; }
+    if (taps) {
+        int rc = stem_half ? add_tap<__half>(c, "stem", reinterpret_cast<const __half*>(cur), (size_t)nb * 112 * 112 * 32)
+                           : add_tap<T>(c, "stem", cur, (size_t)nb * 112 * 112 * 32);
+        if (rc) return rc;
+    }
     for (size_t i = 0; i < c->blocks.size(); ++i) {
         const BlockCfg& b = c->blocks[i];
         const BlockW& w = c->bw[i];
@@ -526,7 +565,42 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
         const bool use_kd = std::is_same<T, __nv_bfloat16>::value && c->use_fused && c->use_tc && c->kd_from > 0 && b.idx >= c->kd_from &&
                             b.has_expand && whenet::fused::dwse_chunk(b.k, b.s, b.hin, b.cexp) > 0;
         if constexpr (sizeof(T) == 2) {
-            if (i == 0 && !did_k1 && c->use_fused && c->dw1_fused && c->dw1.valid) {
+            if (i == 0 && stem_half) {
+              if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                whenet::fused::DwSeParams p{};
+                if (c->tmaps.size() > 512) c->tmaps.clear();
+                const TmapKey ke{100 + b.idx, nb, (const void*)cur}, kw{200 + b.idx, 0, (const void*)w.w_dw16};
+                auto ie = c->tmaps.find(ke);
+                if (ie == c->tmaps.end()) {
+                    CUtensorMap tm;
+                    int rc = make_tmap_kd_e(&tm, cur, nb, b.hin, b.cexp, 32, 16);
+                    if (rc) return rc;
+                    ie = c->tmaps.emplace(ke, tm).first;
+                }
+                auto iw = c->tmaps.find(kw);
+                if (iw == c->tmaps.end()) {
+                    CUtensorMap tm;
+                    int rc = make_tmap_kd_w(&tm, w.w_dw16, 9, b.cexp, 32);
+                    if (rc) return rc;
+                    iw = c->tmaps.emplace(kw, tm).first;
+                }
+                p.tmE = ie->second; p.tmW = iw->second;
+                p.b_dw = w.b_dw_h; p.tflag = c->d_tflag; p.out = D; p.partial = c->d_partial;
+                p.C = b.cexp; p.pad = b.pad; p.Cse = b.cse; p.inv_hw = 1.0f / (float)(b.hout * b.hout);
+                int split = 1;
+                {
+                    const int n_tiles = (b.hin / 14) * (b.hin / 14);
+                    while (split < n_tiles && (long long)nb * split < c->k1_split_ctas) ++split;
+                }
+                snprintf(nm, sizeof nm, "b%02d.dw", b.idx);
+                Scope sc(c, nm, (double)nb * 2.0 * b.hin * b.hin * b.cexp * sizeof(T), 2.0 * nb * (double)b.hout * b.hout * b.k * b.k * b.cexp);
+                int rc = whenet::fused::launch_dwse_spatial<T>(c->stream, p, b.hin, nb, split);
+                if (rc != 0) return fail(WHENET_ECUDA, "KD (block 1) launch failed (rc=%d)", rc);
+                CK(cudaGetLastError());
+                tiles = (b.hin / 14) * (b.hin / 14);
+                did_k1 = true;
+              }
+            } else if (i == 0 && !did_k1 && c->use_fused && c->dw1_fused && c->dw1.valid) {
                 whenet::fused::K1Params p = c->dw1.p;
                 p.in = cur; p.wt_aug = nullptr; p.w_dw = w.w_dw_h; p.b_dw = w.b_dw_h; p.out = D; p.partial = c->d_partial; p.tflag = c->d_tflag;
                 p.w_se1t = w.w_se1t; p.b_se1 = w.b_se1; p.w_se2 = w.w_se2; p.b_se2 = w.b_se2; p.gate = c->d_gate; p.Cse = b.cse;
@@ -547,7 +621,25 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
                                       (long long)nb * b.hin * b.hin, b.cin, b.cexp, b.hin * b.hin, true, true);
                 if (rc) return rc;
                 whenet::fused::DwSeParams p{};
-                p.E = reinterpret_cast<const __half*>(E); p.w16 = reinterpret_cast<const __half*>(w.w_dw16); p.b_dw = w.b_dw_h;
+                {
+                    const int cc = whenet::fused::dwse_chunk(b.k, b.s, b.hin, b.cexp), pw = (b.hout - 1) * b.s + b.k;
+                    if (c->tmaps.size() > 512) c->tmaps.clear();
+                    const TmapKey ke{100 + b.idx, nb, (const void*)E}, kw{200 + b.idx, 0, (const void*)w.w_dw16};
+                    auto ie = c->tmaps.find(ke);
+                    if (ie == c->tmaps.end()) {
+                        CUtensorMap tm;
+                        if ((rc = make_tmap_kd_e(&tm, E, nb, b.hin, b.cexp, cc, pw))) return rc;
+                        ie = c->tmaps.emplace(ke, tm).first;
+                    }
+                    auto iw = c->tmaps.find(kw);
+                    if (iw == c->tmaps.end()) {
+                        CUtensorMap tm;
+                        if ((rc = make_tmap_kd_w(&tm, w.w_dw16, b.k * b.k, b.cexp, cc))) return rc;
+                        iw = c->tmaps.emplace(kw, tm).first;
+                    }
+                    p.tmE = ie->second; p.tmW = iw->second;
+                }
+                p.b_dw = w.b_dw_h; p.tflag = c->d_tflag;
                 p.out = D; p.partial = c->d_partial;
                 p.w_se1t = w.w_se1t; p.b_se1 = w.b_se1; p.w_se2 = w.w_se2; p.b_se2 = w.b_se2; p.gate = c->d_gate; p.Cse = b.cse;
                 p.inv_hw = 1.0f / (float)(b.hout * b.hout);
@@ -683,6 +775,15 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
     if (taps && (rc = add_tap<T>(c, "head", E, (size_t)nb * 49 * 1280))) return rc;
     {
         Scope sc(c, "head.fc_decode", (double)nb * (49.0 * 1280 * sizeof(T) + 12), 2.0 * nb * (1280.0 * 252 + 49 * 1280));
+        if (nb >= 64 && c->head_batch) {
+            // throughput batches: GAP kernel + Dense/decode for four crops per CTA (same bits as the one-CTA-per-crop kernel)
+            constexpr int HB = 4;
+            whenet::head_pool_kernel<T><<<nb, 160, 0, c->stream>>>(E, c->d_pooled);
+            auto kfn = whenet::head_fc_decode_batch_kernel<HB>;
+            const size_t hsm = (size_t)HB * (1280 + 256) * sizeof(float);
+            CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+            kfn<<<(nb + HB - 1) / HB, 512, hsm, c->stream>>>(c->d_pooled, c->w_fct, c->b_fc, d_angles, d_logits, nb);
+        } else
         whenet::head_pool_fc_decode_kernel<T><<<nb, 256, 0, c->stream>>>(E, nullptr, c->w_fct, c->b_fc, d_angles, d_logits,
                                                                          taps ? c->d_pooled : nullptr);
         CK(cudaGetLastError());
@@ -1348,7 +1449,9 @@ int debug_conv_impl(whenet_ctx* c, int use_tc, const float* A, const float* W, c
     CK(cudaMemcpy(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
     if (gate) { CK(cudaMalloc(&dG, (size_t)ncrops * K * 4)); CK(cudaMemcpy(dG, gate, (size_t)ncrops * K * 4, cudaMemcpyHostToDevice)); }
     if (resid) { CK(cudaMalloc(&dR, hR.size() * sizeof(T))); CK(cudaMemcpy(dR, hR.data(), hR.size() * sizeof(T), cudaMemcpyHostToDevice)); }
-    CK(cudaMemset(dO, 0xFF, hO.size() * sizeof(T)));
+    // on the context's stream: a legacy-stream memset is not ordered against kernels of a non-blocking stream and could land on
+    // rows the first tiles had already written (seen once in ~20 runs as NaN rows at the start of the output)
+    CK(cudaMemsetAsync(dO, 0xFF, hO.size() * sizeof(T), c->stream));
     const int saved = c->use_tc;
     c->use_tc = use_tc;
     int rc;
@@ -1548,6 +1651,8 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!strcmp(key, "kd_expand_k2")) { c->kd_expand_k2 = value; return 0; }
     if (!strcmp(key, "kd_tail")) { c->kd_tail = value; return 0; }
     if (!strcmp(key, "se_batch")) { c->se_batch = value; return 0; }
+    if (!strcmp(key, "head_batch")) { c->head_batch = value; return 0; }
+    if (!strcmp(key, "dw1_kd")) { c->dw1_kd = value; return 0; }
     if (!strcmp(key, "chunk")) {
         if (value < 1) return fail(WHENET_EINVAL, "chunk must be >= 1");
         c->chunk = std::min(value, c->max_batch);
