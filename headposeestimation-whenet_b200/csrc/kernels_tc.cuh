@@ -67,11 +67,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 
 // Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): D=f32, A/B = bf16 or f16, both K-major.
-__host__ __device__ inline uint32_t make_idesc(bool is_bf16, int umma_n) {
+__host__ __device__ inline uint32_t make_idesc(bool is_bf16, int umma_n, int b_fmt = -1) {
     uint32_t d = 0;
     d |= 1u << 4;                           // c_format = F32
     d |= (is_bf16 ? 1u : 0u) << 7;          // a_format
-    d |= (is_bf16 ? 1u : 0u) << 10;         // b_format
+    d |= ((b_fmt < 0 ? is_bf16 : b_fmt != 0) ? 1u : 0u) << 10;         // b_format (b_fmt: -1 = as A, 0 = f16, 1 = bf16)
     d |= (uint32_t)(umma_n >> 3) << 17;     // n_dim
     d |= (uint32_t)(BM >> 4) << 24;         // m_dim
     return d;
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(128) pw_tc2_kernel(const T* __restrict__ A, co
 template <typename T>
 int launch_pw_tc2(cudaStream_t stream, int* tflag, const T* A, const void* Wt16, const float* bias, const float* gate, const T* resid,
                   T* out, long long M, int K, int N, int hw, bool swish, int stage_cap = 0, int smem_budget_kb = 54, int min_ctas = 296,
-                  bool out_half = false) {
+                  bool out_half = false, int b_fmt = -1) {
     if (sizeof(T) != 2) return 1;
     if ((K & 7) || (N & 7) || M > 0x7fffffffLL) return 1;
     const bool per_crop = gate && hw >= 784;                 // gate on W, tiles stay inside a crop
@@ -439,7 +439,7 @@ int launch_pw_tc2(cudaStream_t stream, int* tflag, const T* A, const void* Wt16,
     const int umma_n = (n_tile + 15) & ~15;
     int tmem_cols = 32;
     while (tmem_cols < umma_n) tmem_cols <<= 1;
-    const uint32_t idesc = make_idesc(std::is_same<T, __nv_bfloat16>::value, umma_n);
+    const uint32_t idesc = make_idesc(std::is_same<T, __nv_bfloat16>::value, umma_n, b_fmt);
     const int nkb = (K + BK - 1) / BK;
     const size_t stage_bytes = A_STAGE_BYTES + (size_t)umma_n * BK * 2;
     const int gate_crops = per_crop ? 1 : std::min(4, (BM - 1) / hw + 2);      // crops one 128-row tile can touch
@@ -471,6 +471,214 @@ int launch_pw_tc2(cudaStream_t stream, int* tflag, const T* A, const void* Wt16,
     else if (!swish && gate && resid) { if (per_crop) TC2(false, 2, true, false); else TC2(false, 1, true, false); }
     else return 1;
 #undef TC2
+    return 0;
+}
+
+
+// ----------------------------------------------------------------------------- pw_tc3: gated projects of the large maps
+// The gated project convs of blocks 1-5 are streams of tiny GEMMs (K = 32..144, N = 16..40, millions of rows): with one 128-row
+// tile per CTA (pw_tc2) every tile pays TMEM allocation, the gate row, the W copy + its rescale and a cold load -> MMA ->
+// epilogue chain - block 1 ran at 2.2 TB/s.  Here a CTA walks `tpc` consecutive tiles of ONE crop: gate row and W' = bf16(W * g)
+// once per CTA (the same scale8s as pw_tc2's per-crop route, so the results are bit-identical), then a two-deep software
+// pipeline over the tiles: cp.async of tile t+1 and the MMA of tile t (second TMEM accumulator) run under the epilogue of
+// tile t-1.
+template <typename T, bool RESID>
+__global__ void __launch_bounds__(128) pw_tc3_kernel(const T* __restrict__ A, const T* __restrict__ Wt, const float* __restrict__ bias,
+                                                     const float* __restrict__ gate, const T* __restrict__ resid, T* __restrict__ out,
+                                                     int K, int N, int hw, int umma_n, int tmem_cols, int tiles_per_crop, int tpc, int groups,
+                                                     uint32_t idesc, int* tflag) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ int s_abort;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int nkb = (K + BK - 1) / BK, kchunks = K >> 3;
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t w_bytes = (uint32_t)nkb * umma_n * 128, a_bytes = (uint32_t)nkb * A_STAGE_BYTES;
+    const uint32_t sW = smem0, sA = sW + ((w_bytes + 1023u) & ~1023u), sG = sA + 2 * a_bytes;
+    const int nch = N >> 3, pitch16 = nch | 1;
+    uint4* stage = reinterpret_cast<uint4*>(smem_raw + (sG + (((uint32_t)K * 4 + 15u) & ~15u) - smem_u32(smem_raw)));
+    const float inv_nch = 1.0f / (float)nch;
+
+    const int crop = blockIdx.x / groups, g = blockIdx.x - crop * groups;
+    const int t_begin = g * tpc, t_end = min(tiles_per_crop, t_begin + tpc);
+    if (t_begin >= t_end) return;
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1);
+        s_abort = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"((uint32_t)tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // one K block of an operand: 16-byte chunk c of rows r0, r0+16, ... (the mapping pw_tc2 uses; ragged last block: zero fill)
+    auto fill_rows = [&](uint32_t dst, const T* src0, int rows, int kb) {
+        const int kc0 = kb * 8;
+        const int cb = min(8, kchunks - kc0);
+        const int c = tid & 7, r0 = tid >> 3;
+        const uint32_t swz = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((c ^ (r0 & 7)) << 4));
+        const T* src = src0 + (long long)r0 * K + (kc0 + c) * 8;
+        for (int r = r0, i = 0; r < rows; r += 16, ++i)
+            cp_async16_z(dst + swz + i * 2048, c < cb ? src + (long long)i * 16 * K : src0, c < cb);
+    };
+    auto fill_a = [&](int t, int buf) {
+        const int rows_valid = min(BM, hw - t * BM);
+        const T* a0 = A + ((long long)crop * hw + (long long)t * BM) * K;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int kc0 = kb * 8;
+            const int cb = min(8, kchunks - kc0);
+            const int c = tid & 7, r0 = tid >> 3;
+            const uint32_t dst = sA + buf * a_bytes + kb * A_STAGE_BYTES + (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((c ^ (r0 & 7)) << 4));
+            const T* src = a0 + (long long)r0 * K + (kc0 + c) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool valid = c < cb && (r0 + 16 * i) < rows_valid;
+                cp_async16_z(dst + i * 2048, valid ? src + (long long)i * 16 * K : A, valid);
+            }
+        }
+    };
+    {   // gate row of this crop, the whole W, the first A tile
+        const int q = K >> 2;
+        for (int idx = tid; idx < q; idx += 128) cp_async16_z(sG + (uint32_t)idx * 16, gate + (long long)crop * K + idx * 4, true);
+        for (int kb = 0; kb < nkb; ++kb) fill_rows(sW + (uint32_t)kb * umma_n * 128, Wt, umma_n <= N ? umma_n : N, kb);
+        if (umma_n > N) {       // rows N..umma_n-1 of W (padding of the MMA's N): zeros
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            for (int kb = 0; kb < nkb; ++kb)
+                for (int idx = tid; idx < (umma_n - N) * 8; idx += 128) {
+                    const int r = N + (idx >> 3), c = idx & 7;
+                    sts128_(sW + (uint32_t)kb * umma_n * 128 + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)), z);
+                }
+        }
+        fill_a(t_begin, 0);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                         // gate row (copied by all threads) visible
+        // W' = 16-bit(W * g): each thread rescales exactly the chunks it copied
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int kc0 = kb * 8;
+            const int cb = min(8, kchunks - kc0);
+            const int c = tid & 7, r0 = tid >> 3;
+            if (c < cb)
+                for (int r = r0, i = 0; r < N; r += 16, ++i) {
+                    const uint32_t addr = sW + (uint32_t)kb * umma_n * 128 + (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((c ^ (r0 & 7)) << 4)) + i * 2048;
+                    sts128_(addr, scale8s<T>(lds128(addr), sG + (uint32_t)((kc0 + c) * 8) * 4));
+                }
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = s_tmem_base;
+
+    auto epilogue = [&](int t, int buf, int it) {
+        if (!mbar_wait(&mbar[buf], (uint32_t)(it >> 1) & 1u, tflag)) s_abort = 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int rows_valid = min(BM, hw - t * BM);
+        const long long m0 = (long long)crop * hw + (long long)t * BM;
+        const bool row_ok = tid < rows_valid;
+        if (!s_abort) {
+            const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * umma_n);
+            for (int c0 = 0; c0 < N; c0 += 16) {
+                float v[16];
+                tmem_ld16(lane_base + (uint32_t)c0, v);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int n = c0 + h * 8;
+                    if (n >= N) break;
+                    float o[8];
+                    const float4 b0 = *reinterpret_cast<const float4*>(bias + n), b1 = *reinterpret_cast<const float4*>(bias + n + 4);
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = v[h * 8 + j] + bb[j];
+                    if (RESID && row_ok) {
+                        float r[8];
+                        ld8<T>(resid + (m0 + tid) * N + n, r);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] += r[j];
+                    }
+                    st8<T>(reinterpret_cast<T*>(stage + tid * pitch16 + ((c0 >> 3) + h)), o);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (!s_abort)
+            for (int idx = tid; idx < rows_valid * nch; idx += 128) {
+                const int r = fdiv_small(idx, inv_nch), j = idx - r * nch;
+                *reinterpret_cast<uint4*>(out + (m0 + r) * N + j * 8) = stage[r * pitch16 + j];
+            }
+    };
+
+    const int ntiles = t_end - t_begin;
+    for (int it = 0; it < ntiles; ++it) {
+        const int t = t_begin + it, buf = it & 1;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");            // A(t) has landed (this thread's part)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                                // ... everyone's; the store loop of tile t-2 is done with `stage`
+        if (tid == 0 && !s_abort) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int krem = min(BK, K - kb * BK);
+                const int ksteps = (krem + 15) >> 4;
+                const uint64_t ad = make_desc(sA + buf * a_bytes + kb * A_STAGE_BYTES), bd = make_desc(sW + (uint32_t)kb * umma_n * 128);
+                for (int k = 0; k < ksteps; ++k)
+                    umma_f16(tmem_d + (uint32_t)(buf * umma_n), ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            }
+            umma_commit(&mbar[buf]);
+        }
+        if (it >= 1) {
+            // tile t-1: its MMA has finished (mbar) -> its A buffer is free for tile t+1, its accumulator is ready
+            if (!mbar_wait(&mbar[buf ^ 1], (uint32_t)((it - 1) >> 1) & 1u, tflag)) s_abort = 1;
+        }
+        if (it + 1 < ntiles) fill_a(t + 1, buf ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (it >= 1) epilogue(t - 1, buf ^ 1, it - 1);
+    }
+    __syncthreads();            // the store loop of tile n-2 is done with `stage` (inside the loop the barrier at the top does this)
+    epilogue(t_end - 1, (ntiles - 1) & 1, ntiles - 1);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)tmem_cols) : "memory");
+}
+
+// 0 = launched; 1 = shape not covered (caller falls back to pw_tc2)
+template <typename T>
+int launch_pw_tc3(cudaStream_t stream, int* tflag, const T* A, const void* Wt16, const float* bias, const float* gate, const T* resid, T* out,
+                  long long M, int K, int N, int hw) {
+    // K <= 128 (one or two K blocks): measured b01 (K = 32) 0.275 -> 0.170 ms, b02 (K = 96) unchanged, b03 / b04 (K = 144: three blocks,
+    // 96 KB of A buffers, two CTAs per SM) 1.7x SLOWER than pw_tc2
+    if (sizeof(T) != 2 || !gate || hw < 784 || (K & 7) || (N & 7) || K > 64 || N > 64 || M % hw) return 1;
+    const int crops = (int)(M / hw);
+    const int tiles_per_crop = (hw + BM - 1) / BM;
+    int groups = (1536 + crops - 1) / crops;                      // enough CTAs for ~10 per SM
+    if (groups > tiles_per_crop) groups = tiles_per_crop;
+    if (groups < 1) groups = 1;
+    const int tpc = (tiles_per_crop + groups - 1) / groups;
+    groups = (tiles_per_crop + tpc - 1) / tpc;
+    if (tpc < 3) return 1;                                        // nothing to pipeline
+    const int umma_n = (N + 15) & ~15;
+    int tmem_cols = 32;
+    while (tmem_cols < 2 * umma_n) tmem_cols <<= 1;
+    const int nkb = (K + BK - 1) / BK;
+    const uint32_t idesc = make_idesc(std::is_same<T, __nv_bfloat16>::value, umma_n);
+    const size_t w_bytes = ((size_t)nkb * umma_n * 128 + 1023) & ~(size_t)1023;
+    const size_t smem = w_bytes + 2 * (size_t)nkb * A_STAGE_BYTES + (((size_t)K * 4 + 15) & ~(size_t)15) + (size_t)BM * ((size_t)(N >> 3) | 1) * 16 + 1024;
+    if (smem > 200 * 1024) return 1;
+    const T* W = reinterpret_cast<const T*>(Wt16);
+    if (resid) {
+        auto kfn = pw_tc3_kernel<T, true>;
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
+        kfn<<<crops * groups, 128, smem, stream>>>(A, W, bias, gate, resid, out, K, N, hw, umma_n, tmem_cols, tiles_per_crop, tpc, groups, idesc, tflag);
+    } else {
+        auto kfn = pw_tc3_kernel<T, false>;
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
+        kfn<<<crops * groups, 128, smem, stream>>>(A, W, bias, gate, resid, out, K, N, hw, umma_n, tmem_cols, tiles_per_crop, tpc, groups, idesc, tflag);
+    }
     return 0;
 }
 

@@ -42,8 +42,9 @@ extern template int launch_dwse_spatial<__nv_bfloat16>(cudaStream_t, DwSeParams,
 namespace tc {
 #define WHENET_EXTERN_PW(T)                                                                                                         \
     extern template int launch_pw_tc2<T>(cudaStream_t, int*, const T*, const void*, const float*, const float*, const T*, T*, long long, \
-                                         int, int, int, bool, int, int, int, bool);                                                 \
-    extern template int launch_k2<T>(cudaStream_t, const K2Params&, size_t, bool, bool, bool, int, bool);
+                                         int, int, int, bool, int, int, int, bool, int);                                                 \
+    extern template int launch_k2<T>(cudaStream_t, const K2Params&, size_t, bool, bool, bool, int, bool);          \
+    extern template int launch_pw_tc3<T>(cudaStream_t, int*, const T*, const void*, const float*, const float*, const T*, T*, long long, int, int, int);
 WHENET_EXTERN_PW(__nv_bfloat16)
 WHENET_EXTERN_PW(__half)
 #undef WHENET_EXTERN_PW
@@ -165,6 +166,7 @@ struct whenet_ctx {
     int kd_expand_k2 = 1;      // the expand GEMM of the KD route: 1 = persistent K2 kernel, 0 = pw_tc2
     int kd_tail = 0;           // KD computes the SE gate and gates its output itself (1) or leaves both to se_gate + the project conv (0)
     int se_batch = 1;          // batches >= 64: se_gate_batch_kernel (four crops per CTA)
+    int pw3 = 1;               // gated projects with H*W >= 784: pw_tc3 (a CTA walks several tiles of one crop) instead of pw_tc2
     int dw1_kd = 1;            // bf16: the stem writes fp16 and block 1's depthwise runs on KD (spatial tiles, TMA, HFMA2) instead of K1's depthwise half
     int head_batch = 1;        // batches >= 64: GAP kernel + Dense/decode for four crops per CTA
     int kd_from = 7;           // bf16: blocks >= kd_from whose map fits one CTA run expand GEMM (fp16 E through L2) + KD; 0 = off
@@ -462,6 +464,12 @@ int launch_pw(whenet_ctx* c, const char* name, const T* A, const float* W, const
                 if (rc < 0) return fail(WHENET_ECUDA, "K2 launch failed for %s (rc=%d)", name, rc);
             }
             // shape or epilogue not covered by K2 -> pw_tc2 below
+        }
+        if (c->use_tc && Wt16 && gate && hw >= 784 && c->pw3 && !out_half && !swish) {
+            // gated projects of the large maps: several tiles of one crop per CTA (pw_tc3; same bits as pw_tc2's per-crop route)
+            int rc = whenet::tc::launch_pw_tc3<T>(c->stream, c->d_tflag, A, Wt16, bias, gate, resid, out, M, K, N, hw);
+            if (rc == 0) { CK(cudaGetLastError()); return 0; }
+            if (rc < 0) return fail(WHENET_ECUDA, "pw_tc3 launch failed for %s (rc=%d)", name, rc);
         }
         if (c->use_tc && Wt16) {
             int rc = whenet::tc::launch_pw_tc2<T>(c->stream, c->d_tflag, A, Wt16, bias, gate, resid, out, M, K, N, hw, swish, c->pw_stage_cap, c->pw_smem_kb, c->pw_min_ctas, out_half);
@@ -1465,6 +1473,8 @@ int debug_conv_impl(whenet_ctx* c, int use_tc, const float* A, const float* W, c
                 rc = launch_pw<T>(c, "debug.conv1x1", dA, dW, dWt, dB, dG, dR, dO, M, K, N, hw, swish != 0);
                 c->pw_variant = saved_v;
                 c->tmaps2.clear();
+            } else if (use_tc == 5) {
+                rc = whenet::tc::launch_pw_tc3<T>(c->stream, c->d_tflag, dA, dWt, dB, dG, dR, dO, M, K, N, hw);
             } else
             rc = whenet::tc::launch_pw_tc2<T>(c->stream, c->d_tflag, dA, dWt, dB, dG, dR, dO, M, K, N, hw, swish != 0);
         uint16_t* dS = nullptr;
@@ -1653,6 +1663,7 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!strcmp(key, "se_batch")) { c->se_batch = value; return 0; }
     if (!strcmp(key, "head_batch")) { c->head_batch = value; return 0; }
     if (!strcmp(key, "dw1_kd")) { c->dw1_kd = value; return 0; }
+    if (!strcmp(key, "pw3")) { c->pw3 = value; return 0; }
     if (!strcmp(key, "chunk")) {
         if (value < 1) return fail(WHENET_EINVAL, "chunk must be >= 1");
         c->chunk = std::min(value, c->max_batch);

@@ -178,3 +178,22 @@ def test_conv1x1_fp32_split_bf16(K, N, kind):
     assert np.abs(got - ref).max() <= 3e-5 * scale, np.abs(got - ref).max()
     assert np.abs(got - simt).max() <= 3e-5 * scale
     m.close()
+
+
+def test_pw_tc3_matches_pw_tc2_bitwise(net):
+    """pw_tc3 (a CTA walks several 128-row tiles of one crop: gate row and W' = 16-bit(W * g) once per CTA, two-deep pipeline over
+    the tiles) must give the bits of pw_tc2's per-crop route on the block-1 project shape, every tile of every group - the
+    second-to-last tile of a group once raced with the last one for the staging buffer."""
+    K, N, hw, crops = 32, 16, 12544, 70
+    rng = np.random.default_rng(K + N)
+    M = crops * hw
+    A = _bf16_round(rng.standard_normal((M, K)))
+    W = _bf16_round(rng.standard_normal((K, N)) / np.sqrt(K))
+    bias = rng.standard_normal(N).astype(np.float32)
+    gate = rng.uniform(0.1, 1.0, (crops, K)).astype(np.float32)
+    a = net.debug_conv1x1(A, W, bias, gate=gate, hw=hw, swish=False, use_tc=5)
+    b = net.debug_conv1x1(A, W, bias, gate=gate, hw=hw, swish=False, use_tc=2)
+    assert np.array_equal(a, b)
+    ref = _bf16_round(A.astype(np.float64) * np.repeat(gate, hw, axis=0)).astype(np.float64)      # A-side rounding: a bound, not the kernel's W-side rounding
+    ref = ref @ W.astype(np.float64) + bias
+    assert np.abs(a - ref).max() <= 3e-2 * max(1.0, np.abs(ref).max())

@@ -262,6 +262,9 @@ def test_se_batch_and_k2_routes_bitwise(prec, sample_crops, jitter_crops):
     m.set_option("head_batch", 0)                          # one CTA per crop for GAP + Dense + decode
     assert np.array_equal(np.stack(m.get_angle(crops), axis=1), ref)
     m.set_option("head_batch", 1)
+    m.set_option("pw3", 0)                                 # gated projects of the large maps: one tile per CTA (pw_tc2) instead of pw_tc3
+    assert np.array_equal(np.stack(m.get_angle(crops), axis=1), ref)
+    m.set_option("pw3", 1)
     m.set_option("pw_variant", 2)                          # pw_tc2 everywhere
     assert np.array_equal(np.stack(m.get_angle(crops), axis=1), ref)
     m.set_option("pw_variant", 3)                          # K2 everywhere: the gated projects of blocks 1-6 then scale A rows

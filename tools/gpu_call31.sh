@@ -1,0 +1,14 @@
+#!/bin/bash
+# pw_tc3 (gated projects of the large maps, several tiles per CTA): tests, per-kernel times, bench
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_conv1x1.py -m gpu -x -q > gpurun_out/c31_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/c31_pytest.log
+tail -6 gpurun_out/c31_pytest.log
+FULL=1 PRECS=bf16 TCS=1 OPTS=streams=1 timeout 300 python tools/gpu_check.py > gpurun_out/c31_kt.log 2>&1
+grep -E "angles|total kernel|b0[1-6].project" gpurun_out/c31_kt.log
+timeout 300 python bench.py --no-cpu > gpurun_out/c31_bench.json 2> gpurun_out/c31_bench.err
+tail -2 gpurun_out/c31_bench.err; python -c "
+import json
+d=json.loads(open('gpurun_out/c31_bench.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches'])
+"
