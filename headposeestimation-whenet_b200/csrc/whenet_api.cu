@@ -787,6 +787,7 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
             // throughput batches: GAP kernel + Dense/decode for four crops per CTA (same bits as the one-CTA-per-crop kernel)
             constexpr int HB = 4;
             whenet::head_pool_kernel<T><<<nb, 160, 0, c->stream>>>(E, c->d_pooled);
+            c->launches++;                     // two kernels under one profile scope
             auto kfn = whenet::head_fc_decode_batch_kernel<HB>;
             const size_t hsm = (size_t)HB * (1280 + 256) * sizeof(float);
             CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
