@@ -13,7 +13,7 @@ _SIMT_TC = ["kernels_simt.cuh", "kernels_tc.cuh"]
 _ABI = os.path.join("..", "..", "include", "whenet_b200.h")
 # translation unit -> the headers it depends on (a unit is recompiled when it or one of them is newer than its object)
 UNITS = {
-    "whenet_api.cu": _SIMT_TC + ["kernels_fused.cuh", "kernels_crop.cuh", "kernels_k1w.cuh", "kernels_k2.cuh", "kernels_tc32.cuh", "kernels_dwse.cuh", _ABI],
+    "whenet_api.cu": _SIMT_TC + ["kernels_fused.cuh", "kernels_crop.cuh", "kernels_k1w.cuh", "kernels_k2.cuh", "kernels_tc32.cuh", "kernels_dwse.cuh", "kernels_stem_tc.cuh", _ABI],
     "inst_k1_bf16.cu": _SIMT_TC + ["kernels_fused.cuh"],
     "inst_k1_f16.cu": _SIMT_TC + ["kernels_fused.cuh"],
     "inst_k1w.cu": _SIMT_TC + ["kernels_fused.cuh", "kernels_k1w.cuh"],

@@ -24,6 +24,7 @@
 #include "kernels_k2.cuh"
 #include "kernels_tc32.cuh"
 #include "kernels_dwse.cuh"
+#include "kernels_stem_tc.cuh"
 #include <cudaTypedefs.h>
 
 // The fused-kernel launchers are instantiated in their own translation units (inst_k1_bf16.cu, inst_k1_f16.cu, inst_k1x.cu)
@@ -166,6 +167,8 @@ struct whenet_ctx {
     int kd_expand_k2 = 1;      // the expand GEMM of the KD route: 1 = persistent K2 kernel, 0 = pw_tc2
     int kd_tail = 0;           // KD computes the SE gate and gates its output itself (1) or leaves both to se_gate + the project conv (0)
     int se_batch = 1;          // batches >= 64: se_gate_batch_kernel (four crops per CTA)
+    int stem_tc = 0;           // bf16, uint8 input: 1 = the stem as an im2col GEMM on the tensor core (kernels_stem_tc.cuh) instead of 27 x 32 FFMAs
+                               // per pixel.  Correct (stem tap 2e-3 rms-relative: bf16 weights) but not faster: 0.346 vs 0.338 ms per 512 crops
     int pw3 = 1;               // gated projects with H*W >= 784: pw_tc3 (a CTA walks several tiles of one crop) instead of pw_tc2
     int dw1_kd = 1;            // bf16: the stem writes fp16 and block 1's depthwise runs on KD (spatial tiles, TMA, HFMA2) instead of K1's depthwise half
     int head_batch = 1;        // batches >= 64: GAP kernel + Dense/decode for four crops per CTA
@@ -545,7 +548,18 @@ int forward_chunk(whenet_ctx* c, const void* d_in, int nb, float* d_angles, floa
     {
         Scope sc(c, "stem", (double)nb * (kImgElems * (IN_U8 ? 1.0 : 4.0) + 112.0 * 112 * 32 * sizeof(T)),
                  2.0 * nb * 112.0 * 112 * 27 * 32);
-        if (stem_half) {
+        bool stem_done = false;
+        if constexpr (IN_U8 && std::is_same<T, __nv_bfloat16>::value) {
+            if (c->stem_tc && c->use_tc && c->use_fused) {
+                // bf16 throughput mode, uint8 input: the stem as an im2col GEMM on the tensor core (kernels_stem_tc.cuh)
+                const int rc = stem_half ? whenet::launch_stem_tc<__half>(c->stream, (const uint8_t*)d_in, reinterpret_cast<__half*>(cur), c->stem_params, c->lut, c->d_tflag, nb)
+                                         : whenet::launch_stem_tc<T>(c->stream, (const uint8_t*)d_in, cur, c->stem_params, c->lut, c->d_tflag, nb);
+                if (rc != 0) return fail(WHENET_ECUDA, "tensor-core stem launch failed (rc=%d)", rc);
+                stem_done = true;
+            }
+        }
+        if (stem_done) {
+        } else if (stem_half) {
             // block 1's depthwise is KD (HFMA2 over an fp16 tile): the stem output, read by nothing else, is written as fp16
             whenet::stem_tile_kernel<__half, IN_U8, true><<<dim3(56, nb), 224, 0, c->stream>>>(d_in, reinterpret_cast<__half*>(cur), c->stem_params, c->lut);
         } else if (c->stem_variant == 0) {
@@ -1665,6 +1679,7 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!strcmp(key, "head_batch")) { c->head_batch = value; return 0; }
     if (!strcmp(key, "dw1_kd")) { c->dw1_kd = value; return 0; }
     if (!strcmp(key, "pw3")) { c->pw3 = value; return 0; }
+    if (!strcmp(key, "stem_tc")) { c->stem_tc = value; return 0; }
     if (!strcmp(key, "chunk")) {
         if (value < 1) return fail(WHENET_EINVAL, "chunk must be >= 1");
         c->chunk = std::min(value, c->max_batch);
