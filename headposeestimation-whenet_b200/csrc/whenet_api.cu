@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -12,6 +13,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -213,6 +215,10 @@ struct whenet_ctx {
                                    // B200 (round 1): the fence + ticket tail costs more (+0.7 ms / 512 crops) than the 15
                                    // small se_gate launches it saves (0.37 ms), so it is off by default.
     void* d_in[2] = {nullptr, nullptr};
+    void* h_stage = nullptr;            // pinned staging for PAGEABLE host inputs (upload_input)
+    size_t h_stage_bytes = 0;
+    cudaEvent_t ev_stage = nullptr;     // the last H2D copy out of h_stage
+    int stage_threads = 8;              // host threads that fill the staging buffer (0 = plain cudaMemcpyAsync from the pageable buffer)
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     // crop front-end staging
     uint8_t* d_frame = nullptr; size_t frame_cap = 0;
@@ -821,6 +827,69 @@ void drop_graphs(whenet_ctx* c) {
 }
 
 
+// Host -> device upload of an input batch.  Pinned (or registered) buffers go straight to cudaMemcpyAsync.  A PAGEABLE buffer - what
+// the reference's callers pass to get_angle (a plain numpy array, demo.py:12-14) - would be staged by the driver through its own
+// bounce buffer by one thread (~10 GB/s: 7 ms for 512 crops, longer than the whole forward); here `stage_threads` host threads copy
+// 4 MB pieces into the context's pinned staging buffer and each piece starts its DMA as soon as it is staged.
+// `stage_off` / `stage_total`: where this piece of the batch sits in the staging buffer and how large the buffer has to be (the halves
+// of a two-stream forward use disjoint regions, so the second half is staged while the first one is still in flight); `first`:
+// first upload of a forward call - the only one that has to wait for the previous call's DMA out of the staging buffer.
+int upload_input(whenet_ctx* c, void* dst, const void* src, size_t bytes, cudaStream_t stream, size_t stage_off = 0, size_t stage_total = 0,
+                 bool first = true) {
+    constexpr size_t kPiece = 4u << 20;
+    bool pageable = false;
+    if (c->stage_threads > 0 && bytes >= 2 * kPiece) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, src) == cudaSuccess) pageable = at.type == cudaMemoryTypeUnregistered;
+        else cudaGetLastError();
+    }
+    if (!pageable) {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+        return 0;
+    }
+    if (stage_total < stage_off + bytes) stage_total = stage_off + bytes;
+    if (c->h_stage_bytes < stage_total) {
+        if (c->h_stage) { cudaEventSynchronize(c->ev_stage); cudaFreeHost(c->h_stage); c->h_stage = nullptr; c->h_stage_bytes = 0; }
+        if (cudaHostAlloc(&c->h_stage, stage_total, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));       // no pinned memory left: the plain route
+            return 0;
+        }
+        c->h_stage_bytes = stage_total;
+        if (!c->ev_stage) CK(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
+    } else if (first) {
+        CK(cudaEventSynchronize(c->ev_stage));              // the previous call's uploads have left the staging buffer
+    }
+    char* const stage = (char*)c->h_stage + stage_off;
+    const size_t n_pieces = (bytes + kPiece - 1) / kPiece;
+    std::vector<std::atomic<int>> done(n_pieces);
+    for (auto& d : done) d.store(0, std::memory_order_relaxed);
+    std::atomic<size_t> next{0};
+    const int nt = (int)std::min<size_t>((size_t)c->stage_threads, n_pieces);
+    auto work = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1, std::memory_order_relaxed);
+            if (i >= n_pieces) break;
+            const size_t off = i * kPiece, len = std::min(kPiece, bytes - off);
+            memcpy(stage + off, (const char*)src + off, len);
+            done[i].store(1, std::memory_order_release);
+        }
+    };
+    std::vector<std::thread> pool;
+    pool.reserve(nt);
+    for (int t = 0; t < nt; ++t) pool.emplace_back(work);
+    cudaError_t err = cudaSuccess;
+    for (size_t i = 0; i < n_pieces; ++i) {
+        while (!done[i].load(std::memory_order_acquire)) std::this_thread::yield();
+        const size_t off = i * kPiece, len = std::min(kPiece, bytes - off);
+        if (err == cudaSuccess) err = cudaMemcpyAsync((char*)dst + off, stage + off, len, cudaMemcpyHostToDevice, stream);
+    }
+    for (auto& th : pool) th.join();
+    if (err != cudaSuccess) return fail(WHENET_ECUDA, "staged upload failed: %s", cudaGetErrorString(err));
+    CK(cudaEventRecord(c->ev_stage, stream));
+    return 0;
+}
+
 template <typename T, bool IN_U8>
 int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* angles_out, float* logits_out, int out_is_device) {
     int rc = ensure_ws(c);
@@ -862,7 +931,8 @@ int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* a
             if (!in_is_device) {
                 // half h uploads on the copy stream while half h-1 (and the previous call) compute
                 char* dst = (char*)c->d_in[slot] + (size_t)off * kImgElems * in_es;
-                CK(cudaMemcpyAsync(dst, d_src, (size_t)nb * kImgElems * in_es, cudaMemcpyHostToDevice, c->copy_stream));
+                if (int urc = upload_input(c, dst, d_src, (size_t)nb * kImgElems * in_es, c->copy_stream, (size_t)off * kImgElems * in_es,
+                                           (size_t)n * kImgElems * in_es, h == 0)) return urc;
                 CK(cudaEventRecord(c->ev_half[h], c->copy_stream));
                 CK(cudaStreamWaitEvent(c->aux_stream[h], c->ev_half[h], 0));
                 d_src = dst;
@@ -904,8 +974,7 @@ int forward_all(whenet_ctx* c, const void* in, int n, int in_is_device, float* a
         } else {
             // stage through the copy stream so chunk i+1 uploads while chunk i computes
             CK(cudaStreamWaitEvent(c->copy_stream, c->ev_free[slot], 0));
-            CK(cudaMemcpyAsync(c->d_in[slot], (const char*)in + (size_t)off * kImgElems * in_es, (size_t)nb * kImgElems * in_es,
-                               cudaMemcpyHostToDevice, c->copy_stream));
+            if (int urc = upload_input(c, c->d_in[slot], (const char*)in + (size_t)off * kImgElems * in_es, (size_t)nb * kImgElems * in_es, c->copy_stream)) return urc;
             CK(cudaEventRecord(c->ev_ready[slot], c->copy_stream));
             CK(cudaStreamWaitEvent(c->stream, c->ev_ready[slot], 0));
             d_in = c->d_in[slot];
@@ -1680,6 +1749,7 @@ int whenet_set_option(whenet_ctx* c, const char* key, int value) {
     if (!strcmp(key, "dw1_kd")) { c->dw1_kd = value; return 0; }
     if (!strcmp(key, "pw3")) { c->pw3 = value; return 0; }
     if (!strcmp(key, "stem_tc")) { c->stem_tc = value; return 0; }
+    if (!strcmp(key, "stage_threads")) { c->stage_threads = value < 0 ? 0 : (value > 32 ? 32 : value); return 0; }
     if (!strcmp(key, "chunk")) {
         if (value < 1) return fail(WHENET_EINVAL, "chunk must be >= 1");
         c->chunk = std::min(value, c->max_batch);
@@ -1716,6 +1786,8 @@ void whenet_destroy(whenet_ctx* c) {
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->ev_stage) cudaEventDestroy(c->ev_stage);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }

@@ -243,6 +243,32 @@ def test_kd_route(oracle32, sample_crops, jitter_crops):
     m.close()
 
 
+def test_pageable_input_staging(sample_crops, jitter_crops):
+    """get_angle(numpy array) = a PAGEABLE host buffer (the reference's call shape): batches of 8 MB and more are copied into the
+    context's pinned staging buffer by several host threads, piece by piece, each piece starting its DMA as soon as it is staged.
+    Same bits as the plain cudaMemcpyAsync route, for repeated calls, changing sizes and a float32 input."""
+    import whenet_b200
+    crops = np.concatenate([sample_crops, jitter_crops] * 20)[:150]
+    m = whenet_b200.WHENet(SNAP, device=0, precision="bf16", max_batch=256)
+    m.set_option("stage_threads", 0)
+    ref = np.stack(m.get_angle(crops), axis=1)
+    for nt in (8, 1, 3):
+        m.set_option("stage_threads", nt)
+        for n in (150, 70, 150):
+            got = np.stack(m.get_angle(crops[:n]), axis=1)
+            assert np.array_equal(got, ref[:n]), (nt, n)
+    m.set_option("streams", 1)
+    assert np.array_equal(np.stack(m.get_angle(crops), axis=1), ref)
+    m.close()
+    m32 = whenet_b200.WHENet(SNAP, device=0, precision="fp32", max_batch=64)
+    x = crops[:40].astype(np.float32)
+    m32.set_option("stage_threads", 0)
+    a = np.stack(m32.get_angle(x), axis=1)
+    m32.set_option("stage_threads", 4)
+    assert np.array_equal(np.stack(m32.get_angle(x), axis=1), a)
+    m32.close()
+
+
 def test_stem_on_tensor_core_option(oracle32, sample_crops, jitter_crops):
     """Option stem_tc=1 (bf16, uint8 input): the stem as an im2col GEMM on tcgen05 - table lookups build the [hi | lo] bf16
     operand rows in shared memory, TF-SAME padding by masking the taps of the missing row / column 224.  The stem output must
