@@ -646,29 +646,39 @@ __global__ void __launch_bounds__(128) pw_tc3_kernel(const T* __restrict__ A, co
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)tmem_cols) : "memory");
 }
 
+// Which gated projects pw_tc3 takes and how it walks them (host-side, tested without a GPU by tests/test_route_plans.py).
+struct Pw3Plan { int tiles_per_crop, tpc, groups, umma_n, tmem_cols; size_t smem; };
+inline bool plan_pw_tc3(long long M, int K, int N, int hw, bool has_gate, Pw3Plan* pl) {
+    // K <= 64 (one K block): measured b01 (K = 32) 0.275 -> 0.170 ms, b02 (K = 96) unchanged, b03 / b04 (K = 144: three blocks,
+    // 96 KB of A buffers, two CTAs per SM) 1.7x SLOWER than pw_tc2
+    if (!has_gate || hw < 784 || (K & 7) || (N & 7) || K > 64 || N > 64 || M < 1 || M % hw) return false;
+    const int crops = (int)(M / hw);
+    pl->tiles_per_crop = (hw + BM - 1) / BM;
+    int groups = (1536 + crops - 1) / crops;                      // enough CTAs for ~10 per SM
+    if (groups > pl->tiles_per_crop) groups = pl->tiles_per_crop;
+    if (groups < 1) groups = 1;
+    pl->tpc = (pl->tiles_per_crop + groups - 1) / groups;
+    pl->groups = (pl->tiles_per_crop + pl->tpc - 1) / pl->tpc;
+    if (pl->tpc < 3) return false;                                // nothing to pipeline
+    pl->umma_n = (N + 15) & ~15;
+    pl->tmem_cols = 32;
+    while (pl->tmem_cols < 2 * pl->umma_n) pl->tmem_cols <<= 1;
+    const int nkb = (K + BK - 1) / BK;
+    const size_t w_bytes = ((size_t)nkb * pl->umma_n * 128 + 1023) & ~(size_t)1023;
+    pl->smem = w_bytes + 2 * (size_t)nkb * A_STAGE_BYTES + (((size_t)K * 4 + 15) & ~(size_t)15) + (size_t)BM * ((size_t)(N >> 3) | 1) * 16 + 1024;
+    return pl->smem <= 200 * 1024;
+}
+
 // 0 = launched; 1 = shape not covered (caller falls back to pw_tc2)
 template <typename T>
 int launch_pw_tc3(cudaStream_t stream, int* tflag, const T* A, const void* Wt16, const float* bias, const float* gate, const T* resid, T* out,
                   long long M, int K, int N, int hw) {
-    // K <= 128 (one or two K blocks): measured b01 (K = 32) 0.275 -> 0.170 ms, b02 (K = 96) unchanged, b03 / b04 (K = 144: three blocks,
-    // 96 KB of A buffers, two CTAs per SM) 1.7x SLOWER than pw_tc2
-    if (sizeof(T) != 2 || !gate || hw < 784 || (K & 7) || (N & 7) || K > 64 || N > 64 || M % hw) return 1;
+    Pw3Plan pl{};
+    if (sizeof(T) != 2 || !plan_pw_tc3(M, K, N, hw, gate != nullptr, &pl)) return 1;
     const int crops = (int)(M / hw);
-    const int tiles_per_crop = (hw + BM - 1) / BM;
-    int groups = (1536 + crops - 1) / crops;                      // enough CTAs for ~10 per SM
-    if (groups > tiles_per_crop) groups = tiles_per_crop;
-    if (groups < 1) groups = 1;
-    const int tpc = (tiles_per_crop + groups - 1) / groups;
-    groups = (tiles_per_crop + tpc - 1) / tpc;
-    if (tpc < 3) return 1;                                        // nothing to pipeline
-    const int umma_n = (N + 15) & ~15;
-    int tmem_cols = 32;
-    while (tmem_cols < 2 * umma_n) tmem_cols <<= 1;
-    const int nkb = (K + BK - 1) / BK;
+    const int tiles_per_crop = pl.tiles_per_crop, tpc = pl.tpc, groups = pl.groups, umma_n = pl.umma_n, tmem_cols = pl.tmem_cols;
+    const size_t smem = pl.smem;
     const uint32_t idesc = make_idesc(std::is_same<T, __nv_bfloat16>::value, umma_n);
-    const size_t w_bytes = ((size_t)nkb * umma_n * 128 + 1023) & ~(size_t)1023;
-    const size_t smem = w_bytes + 2 * (size_t)nkb * A_STAGE_BYTES + (((size_t)K * 4 + 15) & ~(size_t)15) + (size_t)BM * ((size_t)(N >> 3) | 1) * 16 + 1024;
-    if (smem > 200 * 1024) return 1;
     const T* W = reinterpret_cast<const T*>(Wt16);
     if (resid) {
         auto kfn = pw_tc3_kernel<T, true>;
